@@ -1,0 +1,223 @@
+"""diso_b200 -- B200-native differentiable Marching Cubes / Dual Marching Cubes.
+
+Drop-in for the reference package ``diso`` (``from diso_b200 import DiffMC, DiffDMC``): same
+``torch.nn.Module``s, same ``forward`` signatures and return conventions as
+/root/reference/diso/__init__.py:9-147, fp32/fp64, autograd into ``grid`` and ``deform``.
+
+Host code is Python/PyTorch (tensor allocation, autograd plumbing, streams); all computation is
+in hand-written sm_100a CUDA kernels behind the C ABI of ``include/diso_b200.h``.
+"""
+import torch
+from torch import nn
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import DisoB200Error  # noqa: F401
+
+__all__ = ["DiffMC", "DiffDMC", "extract_counts", "debug_cell_codes", "split_quads"]
+__version__ = "0.1.0"
+
+_DTYPES = {torch.float32: _lib.F32, torch.float64: _lib.F64}
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_inputs(grid, deform, dtype):
+    # mirrors the checks of the reference glue (src/pybind.cpp:5-11,57-60): CUDA tensors of the
+    # extractor's dtype.  Contiguity is not required of the caller (the reference's F.pad makes a
+    # contiguous copy, diso/__init__.py:52); we take a contiguous view/copy only when needed.
+    if not grid.is_cuda:
+        raise DisoB200Error("grid must be a CUDA tensor")
+    if grid.dim() != 3:
+        raise DisoB200Error("grid must be 3-D [X,Y,Z], got shape %s" % (tuple(grid.shape),))
+    if grid.dtype != dtype:
+        raise DisoB200Error("grid type must match the extractor dtype (%s), got %s" % (dtype, grid.dtype))
+    if deform is not None:
+        if not deform.is_cuda or deform.device != grid.device:
+            raise DisoB200Error("deform must be a CUDA tensor on the grid's device")
+        if deform.dtype != dtype:
+            raise DisoB200Error("deformation type must match the extractor dtype (%s), got %s" % (dtype, deform.dtype))
+        if tuple(deform.shape) != tuple(grid.shape) + (3,):
+            raise DisoB200Error("deform must have shape [X,Y,Z,3], got %s" % (tuple(deform.shape),))
+
+
+def _count(alg, grid, isovalue):
+    """Phase 1 + the forward's single host sync.  Returns (state tensor, counts list)."""
+    L = _lib.load()
+    X, Y, Z = grid.shape
+    nbytes = L.diso_b200_state_bytes(alg, X, Y, Z)
+    if nbytes == 0:
+        _lib.check(-1 if not L.diso_b200_last_error() else -4)
+    state = torch.empty(nbytes, dtype=torch.uint8, device=grid.device)
+    _lib.check(L.diso_b200_count(alg, grid.data_ptr(), _DTYPES[grid.dtype], X, Y, Z, float(isovalue),
+                                 state.data_ptr(), nbytes, _stream()))
+    counts = state[: 8 * _lib.COUNT_SLOTS].view(torch.int64).cpu().tolist()  # the one sync
+    return state, counts
+
+
+class _Extract(Function):
+    """autograd node shared by DiffMC / DiffDMC (reference: DMCFunction / DDMCFunction,
+    diso/__init__.py:18-44, 73-98).  Unlike the reference, backward does not re-run the
+    forward: the compact rank structure built by phase 1 is saved in ctx as a tensor, which
+    keeps batch / activation-checkpoint semantics (nothing lives in the extractor object)."""
+
+    @staticmethod
+    def forward(ctx, grid, deform, alg, isovalue, normalize, grad_mode, state, n_verts, n_faces):
+        L = _lib.load()
+        X, Y, Z = grid.shape
+        k = 3 if alg == _lib.ALG_MC else 4
+        verts = torch.empty((n_verts, 3), dtype=grid.dtype, device=grid.device)
+        faces = torch.empty((n_faces, k), dtype=torch.int64, device=grid.device)
+        emit = L.diso_b200_mc_emit if alg == _lib.ALG_MC else L.diso_b200_dmc_emit
+        _lib.check(emit(grid.data_ptr(), _ptr(deform), _DTYPES[grid.dtype], X, Y, Z, float(isovalue),
+                        state.data_ptr(), int(bool(normalize)), verts.data_ptr(), faces.data_ptr(), _stream()))
+        ctx.alg, ctx.isovalue, ctx.normalize, ctx.grad_mode = alg, float(isovalue), bool(normalize), grad_mode
+        ctx.n_edges = n_verts if alg == _lib.ALG_MC else n_faces
+        ctx.save_for_backward(grid, deform, state)
+        ctx.mark_non_differentiable(faces)
+        return verts, faces
+
+    @staticmethod
+    def backward(ctx, adj_verts, adj_faces):
+        grid, deform, state = ctx.saved_tensors
+        L = _lib.load()
+        X, Y, Z = grid.shape
+        if adj_verts is None:
+            adj_verts = torch.zeros((0, 3), dtype=grid.dtype, device=grid.device)
+        # the reference requires a contiguous adj_verts and raises otherwise (pybind.cpp:142);
+        # expanded gradients (e.g. from verts.sum() with normalize=False) are made contiguous here.
+        adj_verts = adj_verts.contiguous()
+        need_grid, need_deform = ctx.needs_input_grad[0], deform is not None
+        with torch.cuda.device(grid.device):
+            adj_grid = torch.empty_like(grid)  # fully written by the kernel, zeros included
+            adj_deform = torch.empty_like(deform) if need_deform else None
+            dt = _DTYPES[grid.dtype]
+            if ctx.alg == _lib.ALG_MC:
+                _lib.check(L.diso_b200_mc_backward(grid.data_ptr(), _ptr(deform), dt, X, Y, Z, ctx.isovalue,
+                                                   state.data_ptr(), adj_verts.data_ptr(), int(ctx.normalize),
+                                                   adj_grid.data_ptr(), _ptr(adj_deform), _stream()))
+            else:
+                scratch = torch.empty((max(ctx.n_edges, 1), 3), dtype=grid.dtype, device=grid.device)
+                _lib.check(L.diso_b200_dmc_backward(grid.data_ptr(), _ptr(deform), dt, X, Y, Z, ctx.isovalue,
+                                                    state.data_ptr(), adj_verts.data_ptr(), int(ctx.normalize),
+                                                    ctx.grad_mode, scratch.data_ptr(), adj_grid.data_ptr(),
+                                                    _ptr(adj_deform), _stream()))
+        del need_grid
+        return adj_grid, adj_deform, None, None, None, None, None, None, None
+
+
+def _run(alg, dtype, grad_mode, grid, deform, isovalue, normalize):
+    _check_inputs(grid, deform, dtype)
+    k = 3 if alg == _lib.ALG_MC else 4
+    with torch.cuda.device(grid.device):
+        g = grid.contiguous()
+        d = deform.contiguous() if deform is not None else None
+        with torch.no_grad():
+            state, counts = _count(alg, g, isovalue)
+        n_verts, n_faces = counts[_lib.CNT_VERTS], counts[_lib.CNT_FACES]
+        # diso/__init__.py:49-50,103-104: empty-surface early-out (min >= iso or max <= iso),
+        # which returns detached (0,3) verts and INT32 (0,3)/(0,4) faces.
+        if counts[_lib.CNT_EDGES] == 0 or counts[_lib.CNT_ANY_GT] == 0:
+            return (torch.zeros((0, 3), dtype=dtype, device=grid.device),
+                    torch.zeros((0, k), dtype=torch.int32, device=grid.device))
+        if max(n_verts, n_faces) >= 2 ** 32 - 1:
+            raise DisoB200Error("mesh too large for one call (%d verts, %d faces): shard the grid" % (n_verts, n_faces))
+        return _Extract.apply(g, d, alg, float(isovalue), bool(normalize), grad_mode, state, n_verts, n_faces)
+
+
+def _grad_mode(name):
+    try:
+        return {"reference": _lib.GRAD_REFERENCE, "exact": _lib.GRAD_EXACT}[name]
+    except KeyError:
+        raise ValueError("grad_mode must be 'reference' or 'exact'") from None
+
+
+class DiffMC(nn.Module):
+    """Differentiable Marching Cubes (reference: diso/__init__.py:9-61).
+
+    forward(grid [X,Y,Z], deform [X,Y,Z,3] | None, isovalue=0.0, normalize=True)
+        -> verts [V,3] (dtype), faces [F,3] (int64)
+    """
+
+    def __init__(self, dtype=torch.float32):
+        super().__init__()
+        if dtype not in _DTYPES:
+            raise DisoB200Error("DiffMC supports torch.float32 / torch.float64, got %s" % (dtype,))
+        self.dtype = dtype
+        _lib.load()  # fail at construction, not first use, if the CUDA library is missing
+
+    def forward(self, grid, deform=None, isovalue=0.0, normalize=True):
+        return _run(_lib.ALG_MC, self.dtype, _lib.GRAD_REFERENCE, grid, deform, isovalue, normalize)
+
+
+class DiffDMC(nn.Module):
+    """Differentiable Dual Marching Cubes (reference: diso/__init__.py:64-147).
+
+    forward(grid, deform=None, isovalue=0.0, return_quads=False, normalize=True)
+        -> verts [V,3] (dtype), faces [F,3] or quads [Q,4] (int64)
+
+    grad_mode: "reference" (default) reproduces the reference's backward bit-for-bug: in
+    cudualmc.cu:957-1005 the dual-vertex cursor is never advanced, so all patches of a cell
+    receive the gradient of the cell's first dual vertex.  "exact" is the true adjoint of the
+    forward.  They differ only for cells with >= 2 patches.
+    """
+
+    def __init__(self, dtype=torch.float32, grad_mode="reference"):
+        super().__init__()
+        if dtype not in _DTYPES:
+            raise DisoB200Error("DiffDMC supports torch.float32 / torch.float64, got %s" % (dtype,))
+        self.dtype = dtype
+        self.grad_mode = grad_mode
+        _grad_mode(grad_mode)
+        _lib.load()
+
+    def forward(self, grid, deform=None, isovalue=0.0, return_quads=False, normalize=True):
+        verts, quads = _run(_lib.ALG_DMC, self.dtype, _grad_mode(self.grad_mode), grid, deform, isovalue, normalize)
+        if return_quads or quads.shape[0] == 0:
+            # (the reference's early-out returns the (0,4) int32 tensor even when triangles were asked for)
+            return verts, quads
+        return verts, split_quads(verts.detach(), quads)
+
+
+def split_quads(verts, quads):
+    """Quad -> triangle split of diso/__init__.py:118-147 (max-min-angle diagonal, config-1 quads
+    first) as one fused CUDA pass.  verts [V,3] float32/64, quads [Q,4] int64 -> faces [2Q,3] int64."""
+    L = _lib.load()
+    verts = verts.contiguous()
+    quads = quads.contiguous()
+    nq = quads.shape[0]
+    faces = torch.empty((2 * nq, 3), dtype=torch.int64, device=quads.device)
+    if nq == 0:
+        return faces
+    with torch.cuda.device(quads.device):
+        scratch = torch.empty(L.diso_b200_quad_split_scratch_bytes(nq), dtype=torch.uint8, device=quads.device)
+        _lib.check(L.diso_b200_quad_split(verts.data_ptr(), _DTYPES[verts.dtype], quads.data_ptr(), nq,
+                                          scratch.data_ptr(), faces.data_ptr(), _stream()))
+    return faces
+
+
+def extract_counts(alg, grid, isovalue=0.0):
+    """Diagnostics: run phase 1 only; returns dict of counts (verts, faces, edges, used cells)."""
+    alg_id = {"mc": _lib.ALG_MC, "dmc": _lib.ALG_DMC}[alg]
+    with torch.cuda.device(grid.device):
+        _, c = _count(alg_id, grid.contiguous(), isovalue)
+    return dict(verts=c[_lib.CNT_VERTS], faces=c[_lib.CNT_FACES], any_gt=c[_lib.CNT_ANY_GT],
+                edges=c[_lib.CNT_EDGES], used=c[_lib.CNT_USED])
+
+
+def debug_cell_codes(alg, grid, isovalue=0.0):
+    """Diagnostics / parity tests: dense uint8 case index of every padded cell [X+2,Y+2,Z+2]."""
+    L = _lib.load()
+    alg_id = {"mc": _lib.ALG_MC, "dmc": _lib.ALG_DMC}[alg]
+    X, Y, Z = grid.shape
+    with torch.cuda.device(grid.device):
+        state, _ = _count(alg_id, grid.contiguous(), isovalue)
+        codes = torch.empty((X + 2, Y + 2, Z + 2), dtype=torch.uint8, device=grid.device)
+        _lib.check(L.diso_b200_debug_cell_codes(alg_id, X, Y, Z, state.data_ptr(), codes.data_ptr(), _stream()))
+    return codes

@@ -1,0 +1,64 @@
+"""ctypes binding of the C ABI declared in include/diso_b200.h.
+
+This is the stub a maintainer of the reference would write in place of ``from . import _C``
+(/root/reference/diso/__init__.py:6).  There is NO fallback: if the shared library is missing
+or cannot be loaded the import of the operators fails loudly.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdiso_b200.so")
+
+ALG_MC, ALG_DMC = 0, 1
+F32, F64 = 0, 1
+GRAD_REFERENCE, GRAD_EXACT = 0, 1
+COUNT_SLOTS = 8
+CNT_VERTS, CNT_FACES, CNT_ANY_GT, CNT_EDGES, CNT_USED = 0, 1, 2, 3, 4
+
+# every symbol include/diso_b200.h declares: name -> (restype, argtypes)
+_vp, _i, _d, _sz, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t, ctypes.c_int64
+SIGNATURES = {
+    "diso_b200_abi_version": (_i, []),
+    "diso_b200_last_error": (ctypes.c_char_p, []),
+    "diso_b200_state_bytes": (_sz, [_i, _i, _i, _i]),
+    "diso_b200_count": (_i, [_i, _vp, _i, _i, _i, _i, _d, _vp, _sz, _vp]),
+    "diso_b200_mc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _i, _vp, _vp, _vp]),
+    "diso_b200_dmc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _i, _vp, _vp, _vp]),
+    "diso_b200_mc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp]),
+    "diso_b200_dmc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "diso_b200_quad_split_scratch_bytes": (_sz, [_i64]),
+    "diso_b200_quad_split": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp]),
+    "diso_b200_debug_cell_codes": (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+class DisoB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load libdiso_b200.so (once).  Raises if it has not been built -- never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DisoB200Error(
+                "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `python -m diso_b200._build` (requires nvcc); there is no CPU fallback" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.diso_b200_abi_version() != 1:
+            raise DisoB200Error("libdiso_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().diso_b200_last_error().decode("utf-8", "replace")
+        raise DisoB200Error("libdiso_b200 error %d: %s" % (rc, msg))

@@ -1,0 +1,323 @@
+// api.cu -- C ABI of libdiso_b200.so: argument checking, state layout, kernel launches.
+// See include/diso_b200.h for the contract and the reference interfaces each entry replaces.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "classify.cuh"
+#include "dmc.cuh"
+#include "mc.cuh"
+#include "quad_split.cuh"
+
+using namespace diso;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess) return fail(DISO_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define CU_LAUNCH_CHECK(name)                                                                        \
+    do {                                                                                             \
+        cudaError_t e_ = cudaGetLastError();                                                         \
+        if (e_ != cudaSuccess) return fail(DISO_E_CUDA, "launch %s: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+int check_dims(int alg, int dtype, int X, int Y, int Z)
+{
+    if (alg != DISO_ALG_MC && alg != DISO_ALG_DMC) return fail(DISO_E_INVALID, "unknown alg %d", alg);
+    if (dtype != DISO_F32 && dtype != DISO_F64) return fail(DISO_E_INVALID, "unknown dtype %d", dtype);
+    if (X < 1 || Y < 1 || Z < 1) return fail(DISO_E_INVALID, "grid dims must be >= 1 (got %d,%d,%d)", X, Y, Z);
+    // 32-bit budget: padded point count and worst-case crossing-edge count must fit in int32/uint32
+    const double pts = (double)(X + 2) * (Y + 2) * (Z + 2);
+    if (pts >= 1.4e9) return fail(DISO_E_TOOLARGE, "grid %dx%dx%d exceeds the per-call index budget; shard it into slabs", X, Y, Z);
+    return DISO_OK;
+}
+
+struct StatePtrs {
+    long long *counts;
+    unsigned *ticket;
+    TileDesc *desc;
+    unsigned *S;
+    uint4 *E;
+    void *aux;
+};
+
+StatePtrs state_ptrs(void *state, const StateLayout &L)
+{
+    char *b = static_cast<char *>(state);
+    StatePtrs p;
+    p.counts = reinterpret_cast<long long *>(b + L.off_counts);
+    p.ticket = reinterpret_cast<unsigned *>(b + L.off_ticket);
+    p.desc = reinterpret_cast<TileDesc *>(b + L.off_desc);
+    p.S = reinterpret_cast<unsigned *>(b + L.off_sign);
+    p.E = reinterpret_cast<uint4 *>(b + L.off_erec);
+    p.aux = b + L.off_aux;
+    return p;
+}
+
+template <typename T> Epilogue<T> make_epilogue(const Geo &g, int normalize)
+{
+    Epilogue<T> e;
+    e.dx = T(g.X) - T(1);
+    e.dy = T(g.Y) - T(1);
+    e.dz = T(g.Z) - T(1);
+    e.normalize = normalize != 0;
+    return e;
+}
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- phase 1 ---------------------------------------------------------------------------------
+template <typename T>
+int count_impl(int alg, const T *sdf, const Geo &g, double iso, const StateLayout &L, const StatePtrs &p, cudaStream_t st)
+{
+    // header (counts, ticket, tile descriptors) = 0; sign tail = ones; record tails = 0
+    CU_TRY(cudaMemsetAsync(p.counts, 0, L.off_sign - L.off_counts, st));
+    CU_TRY(cudaMemsetAsync(p.S + g.NCH, 0xff, (size_t)L.sign_tail * 4, st));
+    CU_TRY(cudaMemsetAsync(p.E + g.NCH, 0, (size_t)L.rec_tail * 16, st));
+    if (alg == DISO_ALG_MC) CU_TRY(cudaMemsetAsync(reinterpret_cast<unsigned *>(p.aux) + g.NCH, 0, 8 * 4, st));
+    else CU_TRY(cudaMemsetAsync(reinterpret_cast<uint4 *>(p.aux) + g.NCH, 0, (size_t)L.rec_tail * 16, st));
+
+    const T isoT = (T)iso;
+    const int warps = 8;
+    const bool vec4 = sizeof(T) == 4 && (g.Z % 4 == 0) && ((reinterpret_cast<uintptr_t>(sdf) & 15) == 0);
+    if (vec4) {
+        const int NA = (g.Z + 31) / 32;
+        const size_t smem = (size_t)warps * (NA + 2) * 4;
+        sign_pack_f32x4_kernel<<<cdiv(g.NR, warps), warps * 32, smem, st>>>(reinterpret_cast<const float *>(sdf), g,
+                                                                          (float)isoT, p.S, p.counts);
+    } else {
+        sign_pack_kernel<T><<<cdiv(g.NR, warps), warps * 32, 0, st>>>(sdf, g, isoT, p.S, p.counts);
+    }
+    CU_LAUNCH_CHECK("sign_pack");
+    if (alg == DISO_ALG_MC)
+        classify_scan_kernel<DISO_ALG_MC><<<L.n_tiles, SCAN_TILE, 0, st>>>(g, p.S, p.E, p.aux, p.desc, p.ticket, p.counts);
+    else
+        classify_scan_kernel<DISO_ALG_DMC><<<L.n_tiles, SCAN_TILE, 0, st>>>(g, p.S, p.E, p.aux, p.desc, p.ticket, p.counts);
+    CU_LAUNCH_CHECK("classify_scan");
+    return DISO_OK;
+}
+
+template <typename T>
+int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, int normalize, T *verts,
+                 long long *tris, cudaStream_t st)
+{
+    const int groups = cdiv(g.NCH, 32);
+    const int grid = cdiv(groups, EMIT_WARPS);
+    const T isoT = (T)iso, padv = (T)(iso + 1.0);
+    mc_emit_verts_kernel<T><<<grid, EMIT_WARPS * 32, 0, st>>>(sdf, deform, g, isoT, padv, make_epilogue<T>(g, normalize), p.E, verts);
+    CU_LAUNCH_CHECK("mc_emit_verts");
+    mc_emit_tris_kernel<<<grid, EMIT_WARPS * 32, 0, st>>>(g, p.S, p.E, reinterpret_cast<const unsigned *>(p.aux), tris);
+    CU_LAUNCH_CHECK("mc_emit_tris");
+    return DISO_OK;
+}
+
+template <typename T>
+int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, int normalize, T *verts,
+                  long long *quads, cudaStream_t st)
+{
+    const int groups = cdiv(g.NCH, 32);
+    const int grid = cdiv(groups, EMIT_WARPS);
+    const T isoT = (T)iso, padv = (T)(iso + 1.0);
+    const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
+    dmc_emit_verts_kernel<T><<<grid, EMIT_WARPS * 32, 0, st>>>(sdf, deform, g, isoT, padv, make_epilogue<T>(g, normalize), p.S, P, verts);
+    CU_LAUNCH_CHECK("dmc_emit_verts");
+    dmc_edges_kernel<T, 0><<<grid, EMIT_WARPS * 32, 0, st>>>(g, p.S, p.E, P, make_epilogue<T>(g, 0), nullptr, quads, nullptr);
+    CU_LAUNCH_CHECK("dmc_emit_quads");
+    return DISO_OK;
+}
+
+template <typename T>
+int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const T *adj_verts,
+                     int normalize, T *adj_sdf, T *adj_deform, cudaStream_t st)
+{
+    const T isoT = (T)iso, padv = (T)(iso + 1.0);
+    mc_backward_kernel<T><<<cdiv(g.NCH, EMIT_WARPS), EMIT_WARPS * 32, 0, st>>>(sdf, deform, g, isoT, padv, make_epilogue<T>(g, normalize),
+                                                                             p.E, adj_verts, adj_sdf, adj_deform);
+    CU_LAUNCH_CHECK("mc_backward");
+    return DISO_OK;
+}
+
+template <typename T>
+int dmc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const T *adj_verts,
+                      int normalize, int grad_mode, T *scratch, T *adj_sdf, T *adj_deform, cudaStream_t st)
+{
+    const int groups = cdiv(g.NCH, 32);
+    const int grid = cdiv(groups, EMIT_WARPS);
+    const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
+    if (grad_mode == DISO_GRAD_EXACT)
+        dmc_edges_kernel<T, 1><<<grid, EMIT_WARPS * 32, 0, st>>>(g, p.S, p.E, P, make_epilogue<T>(g, normalize), adj_verts, nullptr, scratch);
+    else
+        dmc_edges_kernel<T, 2><<<grid, EMIT_WARPS * 32, 0, st>>>(g, p.S, p.E, P, make_epilogue<T>(g, normalize), adj_verts, nullptr, scratch);
+    CU_LAUNCH_CHECK("dmc_edge_adjoint");
+    return mc_backward_impl<T>(sdf, deform, g, iso, p, scratch, 0, adj_sdf, adj_deform, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int diso_b200_abi_version(void) { return DISO_B200_ABI_VERSION; }
+
+const char *diso_b200_last_error(void) { return g_err; }
+
+size_t diso_b200_state_bytes(int alg, int X, int Y, int Z)
+{
+    if (check_dims(alg, DISO_F32, X, Y, Z) != DISO_OK) return 0;
+    return make_layout(alg, make_geo(X, Y, Z)).total;
+}
+
+int diso_b200_count(int alg, const void *sdf, int dtype, int X, int Y, int Z, double iso, void *state,
+                    size_t state_bytes, void *stream)
+{
+    int rc = check_dims(alg, dtype, X, Y, Z);
+    if (rc) return rc;
+    if (!sdf || !state) return fail(DISO_E_INVALID, "null pointer");
+    const Geo g = make_geo(X, Y, Z);
+    const StateLayout L = make_layout(alg, g);
+    if (state_bytes < L.total) return fail(DISO_E_STATE, "state buffer too small: %zu < %zu", state_bytes, L.total);
+    if (reinterpret_cast<uintptr_t>(state) & 255) return fail(DISO_E_STATE, "state buffer must be 256-byte aligned");
+    const StatePtrs p = state_ptrs(state, L);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == DISO_F32) return count_impl<float>(alg, static_cast<const float *>(sdf), g, iso, L, p, st);
+    return count_impl<double>(alg, static_cast<const double *>(sdf), g, iso, L, p, st);
+}
+
+int diso_b200_mc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
+                      const void *state, int normalize, void *verts, int64_t *tris, void *stream)
+{
+    int rc = check_dims(DISO_ALG_MC, dtype, X, Y, Z);
+    if (rc) return rc;
+    if (!sdf || !state || !verts || !tris) return fail(DISO_E_INVALID, "null pointer");
+    const Geo g = make_geo(X, Y, Z);
+    const StatePtrs p = state_ptrs(const_cast<void *>(state), make_layout(DISO_ALG_MC, g));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == DISO_F32)
+        return mc_emit_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, normalize,
+                                   static_cast<float *>(verts), reinterpret_cast<long long *>(tris), st);
+    return mc_emit_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, normalize,
+                                static_cast<double *>(verts), reinterpret_cast<long long *>(tris), st);
+}
+
+int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
+                       const void *state, int normalize, void *verts, int64_t *quads, void *stream)
+{
+    int rc = check_dims(DISO_ALG_DMC, dtype, X, Y, Z);
+    if (rc) return rc;
+    if (!sdf || !state || !verts || !quads) return fail(DISO_E_INVALID, "null pointer");
+    const Geo g = make_geo(X, Y, Z);
+    const StatePtrs p = state_ptrs(const_cast<void *>(state), make_layout(DISO_ALG_DMC, g));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == DISO_F32)
+        return dmc_emit_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, normalize,
+                                    static_cast<float *>(verts), reinterpret_cast<long long *>(quads), st);
+    return dmc_emit_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, normalize,
+                                 static_cast<double *>(verts), reinterpret_cast<long long *>(quads), st);
+}
+
+int diso_b200_mc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
+                          const void *state, const void *adj_verts, int normalize, void *adj_sdf, void *adj_deform,
+                          void *stream)
+{
+    int rc = check_dims(DISO_ALG_MC, dtype, X, Y, Z);
+    if (rc) return rc;
+    if (!sdf || !state || !adj_verts || !adj_sdf) return fail(DISO_E_INVALID, "null pointer");
+    if ((deform == nullptr) != (adj_deform == nullptr)) return fail(DISO_E_INVALID, "deform and adj_deform must both be given or both be NULL");
+    const Geo g = make_geo(X, Y, Z);
+    const StatePtrs p = state_ptrs(const_cast<void *>(state), make_layout(DISO_ALG_MC, g));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == DISO_F32)
+        return mc_backward_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p,
+                                       static_cast<const float *>(adj_verts), normalize, static_cast<float *>(adj_sdf),
+                                       static_cast<float *>(adj_deform), st);
+    return mc_backward_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p,
+                                    static_cast<const double *>(adj_verts), normalize, static_cast<double *>(adj_sdf),
+                                    static_cast<double *>(adj_deform), st);
+}
+
+int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
+                           const void *state, const void *adj_verts, int normalize, int grad_mode, void *scratch,
+                           void *adj_sdf, void *adj_deform, void *stream)
+{
+    int rc = check_dims(DISO_ALG_DMC, dtype, X, Y, Z);
+    if (rc) return rc;
+    if (!sdf || !state || !adj_verts || !adj_sdf || !scratch) return fail(DISO_E_INVALID, "null pointer");
+    if ((deform == nullptr) != (adj_deform == nullptr)) return fail(DISO_E_INVALID, "deform and adj_deform must both be given or both be NULL");
+    if (grad_mode != DISO_GRAD_REFERENCE && grad_mode != DISO_GRAD_EXACT) return fail(DISO_E_INVALID, "unknown grad_mode %d", grad_mode);
+    const Geo g = make_geo(X, Y, Z);
+    const StatePtrs p = state_ptrs(const_cast<void *>(state), make_layout(DISO_ALG_DMC, g));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == DISO_F32)
+        return dmc_backward_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p,
+                                        static_cast<const float *>(adj_verts), normalize, grad_mode, static_cast<float *>(scratch),
+                                        static_cast<float *>(adj_sdf), static_cast<float *>(adj_deform), st);
+    return dmc_backward_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p,
+                                     static_cast<const double *>(adj_verts), normalize, grad_mode, static_cast<double *>(scratch),
+                                     static_cast<double *>(adj_sdf), static_cast<double *>(adj_deform), st);
+}
+
+size_t diso_b200_quad_split_scratch_bytes(int64_t n_quads)
+{
+    if (n_quads < 0) return 0;
+    const size_t tiles = (size_t)((n_quads + QS_TILE - 1) / QS_TILE);
+    // [0,256): u64 total ; tile offsets (u32 each, 256-byte aligned) ; flags (1 byte per quad)
+    return 256 + align_up(tiles * 4 + 4, 256) + align_up((size_t)n_quads + 1, 256);
+}
+
+int diso_b200_quad_split(const void *verts, int dtype, const int64_t *quads, int64_t n_quads, void *scratch,
+                         int64_t *faces, void *stream)
+{
+    if (dtype != DISO_F32 && dtype != DISO_F64) return fail(DISO_E_INVALID, "unknown dtype %d", dtype);
+    if (n_quads < 0) return fail(DISO_E_INVALID, "negative n_quads");
+    if (n_quads == 0) return DISO_OK;
+    if (n_quads >= (1ll << 32) - 1) return fail(DISO_E_TOOLARGE, "too many quads for one call");
+    if (!verts || !quads || !scratch || !faces) return fail(DISO_E_INVALID, "null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int tiles = cdiv(n_quads, QS_TILE);
+    char *b = static_cast<char *>(scratch);
+    unsigned long long *total = reinterpret_cast<unsigned long long *>(b);
+    unsigned *tile_cnt = reinterpret_cast<unsigned *>(b + 256);
+    unsigned char *flags = reinterpret_cast<unsigned char *>(b + 256 + align_up((size_t)tiles * 4 + 4, 256));
+    const long long *qd = reinterpret_cast<const long long *>(quads);
+    if (dtype == DISO_F32) quad_diag_kernel<float><<<tiles, QS_TILE, 0, st>>>(static_cast<const float *>(verts), qd, n_quads, flags, tile_cnt);
+    else quad_diag_kernel<double><<<tiles, QS_TILE, 0, st>>>(static_cast<const double *>(verts), qd, n_quads, flags, tile_cnt);
+    CU_LAUNCH_CHECK("quad_diag");
+    tile_scan_kernel<<<1, 1024, 0, st>>>(tile_cnt, tiles, total);
+    CU_LAUNCH_CHECK("tile_scan");
+    quad_emit_kernel<<<tiles, QS_TILE, 0, st>>>(qd, n_quads, flags, tile_cnt, total, reinterpret_cast<long long *>(faces));
+    CU_LAUNCH_CHECK("quad_emit");
+    return DISO_OK;
+}
+
+int diso_b200_debug_cell_codes(int alg, int X, int Y, int Z, const void *state, uint8_t *codes, void *stream)
+{
+    int rc = check_dims(alg, DISO_F32, X, Y, Z);
+    if (rc) return rc;
+    if (!state || !codes) return fail(DISO_E_INVALID, "null pointer");
+    const Geo g = make_geo(X, Y, Z);
+    const StatePtrs p = state_ptrs(const_cast<void *>(state), make_layout(alg, g));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long n = (long long)g.PX * g.PY * g.PZ;
+    if (alg == DISO_ALG_MC)
+        debug_codes_kernel<DISO_ALG_MC><<<cdiv(n, 256), 256, 0, st>>>(g, p.S, nullptr, codes);
+    else
+        debug_codes_kernel<DISO_ALG_DMC><<<cdiv(n, 256), 256, 0, st>>>(g, p.S, reinterpret_cast<const uint4 *>(p.aux), codes);
+    CU_LAUNCH_CHECK("debug_codes");
+    return DISO_OK;
+}
+
+}  // extern "C"

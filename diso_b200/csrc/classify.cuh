@@ -1,0 +1,326 @@
+// classify.cuh -- phase 1 of the forward: sign packing and the fused count + single-pass scan.
+//
+// Replaces (reference): count_used_cells_kernel + cub::ExclusiveSum + index_used_cells_kernel
+// + count_cell_mc_verts_kernel + cub::ExclusiveSum + count_cell_mc_tris_kernel /
+// count_cell_patches_kernel + cub::ExclusiveSum  (cumc.cu:265-341,540-562,661-723;
+// cudualmc.cu:605-681,815-863,1068-1122) and the two full-grid min/max reductions of
+// diso/__init__.py:49.
+//
+//   K1 sign_pack      : streams the SDF once (the only compulsory dense read of phase 1),
+//                       emits 1 bit per padded point.  HBM-bound: G*s bytes in, G/8 out.
+//   K2 classify_scan  : one THREAD per 32-point chunk, bit-parallel over lane masks that
+//                       live in L2 (G/8 bytes); counts crossing edges / triangles / patches
+//                       and scans them with a decoupled look-back across 256-chunk tiles.
+#pragma once
+#include "common.cuh"
+#include "tables.cuh"
+
+namespace diso {
+
+// ------------------------------------------------------------------------------------------
+// K1: one warp per padded z-row.  Lane j of iteration c looks at padded point zp = 32c + j.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) sign_pack_kernel(const T *__restrict__ sdf, Geo g, T iso,
+                                                        unsigned *__restrict__ S,
+                                                        long long *__restrict__ counts)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int row = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+    if (row >= g.NR) return;
+    const int xp = row / g.PY, yp = row - xp * g.PY;
+    unsigned *out = S + (size_t)row * g.NC;
+    const bool real_row = xp >= 1 && xp <= g.X && yp >= 1 && yp <= g.Y;
+    if (!real_row) {
+        for (int c = lane; c < g.NC; c += 32) out[c] = FULL;
+        return;
+    }
+    const T *rowp = sdf + ((size_t)(xp - 1) * g.Y + (yp - 1)) * g.Z;
+    bool any_gt = false;
+    unsigned mine = FULL;
+    for (int c0 = 0; c0 < g.NC; c0 += 32) {
+        const int cend = min(32, g.NC - c0);
+#pragma unroll 4
+        for (int cc = 0; cc < cend; ++cc) {
+            const int z = 32 * (c0 + cc) + lane - 1;
+            const bool in = (unsigned)z < (unsigned)g.Z;
+            bool b = true;
+            if (in) {
+                T v = __ldcs(rowp + z);  // streamed: this pass never re-reads a value
+                b = v >= iso;
+                any_gt |= v > iso;
+            }
+            unsigned w = __ballot_sync(FULL, b);
+            if (lane == cc) mine = w;
+        }
+        if (lane < cend) out[c0 + lane] = mine;
+    }
+    if (__any_sync(FULL, any_gt) && lane == 0) counts[DISO_CNT_ANY_GT] = 1;
+}
+
+// Vectorised K1 for fp32 rows whose length is a multiple of 4 and 16-byte aligned: each lane
+// loads one float4 (128-bit), i.e. a warp consumes 512 contiguous bytes per instruction.
+// The 4-bit nibbles are merged into aligned 32-bit words inside 8-lane groups with three
+// shuffle-OR steps, staged in shared memory, then shifted by the one-point pad offset.
+__global__ void __launch_bounds__(256) sign_pack_f32x4_kernel(const float *__restrict__ sdf, Geo g,
+                                                              float iso, unsigned *__restrict__ S,
+                                                              long long *__restrict__ counts)
+{
+    extern __shared__ unsigned sm_words[];  // per warp: NA+1 aligned words
+    const int lane = threadIdx.x & 31;
+    const int wid = threadIdx.x >> 5;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int row = blockIdx.x * warps_per_cta + wid;
+    if (row >= g.NR) return;
+    const int xp = row / g.PY, yp = row - xp * g.PY;
+    unsigned *out = S + (size_t)row * g.NC;
+    const bool real_row = xp >= 1 && xp <= g.X && yp >= 1 && yp <= g.Y;
+    if (!real_row) {
+        for (int c = lane; c < g.NC; c += 32) out[c] = FULL;
+        return;
+    }
+    const int NA = (g.Z + 31) / 32;  // aligned words covering z = 0..Z-1
+    unsigned *aw = sm_words + wid * (NA + 2);
+    const float4 *rowp = reinterpret_cast<const float4 *>(sdf + ((size_t)(xp - 1) * g.Y + (yp - 1)) * g.Z);
+    const int nvec = g.Z >> 2;
+    bool any_gt = false;
+    for (int v0 = 0; v0 < nvec; v0 += 32) {
+        const int v = v0 + lane;
+        unsigned nib = 0xfu;  // beyond the row: ones (pad)
+        if (v < nvec) {
+            float4 q = __ldcs(rowp + v);
+            nib = (q.x >= iso ? 1u : 0u) | (q.y >= iso ? 2u : 0u) | (q.z >= iso ? 4u : 0u) | (q.w >= iso ? 8u : 0u);
+            any_gt |= (q.x > iso) | (q.y > iso) | (q.z > iso) | (q.w > iso);
+        }
+        unsigned w = nib << (4 * (lane & 7));
+        w |= __shfl_xor_sync(FULL, w, 1);
+        w |= __shfl_xor_sync(FULL, w, 2);
+        w |= __shfl_xor_sync(FULL, w, 4);
+        const int widx = (v0 >> 3) + (lane >> 3);  // aligned word index: 8 float4 per word
+        if ((lane & 7) == 0 && widx < NA) aw[widx] = w;
+    }
+    __syncwarp();
+    // padded word c covers z = 32c-1 .. 32c+30  ->  (aligned[c] << 1) | (aligned[c-1] >> 31)
+    for (int c = lane; c < g.NC; c += 32) {
+        unsigned cur = c < NA ? aw[c] : FULL;
+        unsigned prev = c > 0 ? aw[c - 1] : FULL;
+        out[c] = (cur << 1) | (prev >> 31);
+    }
+    if (__any_sync(FULL, any_gt) && lane == 0) counts[DISO_CNT_ANY_GT] = 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Cell case index from lane masks.  Words: A=(x,y) B=(x+1,y) C=(x+1,y+1) D=(x,y+1); the *1
+// variants are the same rows one point further in z.
+//   MC  corner order (cumc.cu:107)       : 000,100,110,010,001,101,111,011 -> A B C D A1 B1 C1 D1
+//   DMC corner order (cudualmc.cu:95-104): 000,100,010,110,001,101,011,111 -> A B D C A1 B1 D1 C1
+// ------------------------------------------------------------------------------------------
+struct CellWords {
+    unsigned A, B, C, D, A1, B1, C1, D1;
+};
+
+__device__ __forceinline__ CellWords load_cell_words(const unsigned *__restrict__ S, const Geo &g, int k)
+{
+    CellWords w;
+    unsigned a = S[k], an = S[k + 1];
+    unsigned d = S[k + g.sY], dn = S[k + g.sY + 1];
+    unsigned b = S[k + g.sX], bn = S[k + g.sX + 1];
+    unsigned c = S[k + g.sX + g.sY], cn = S[k + g.sX + g.sY + 1];
+    w.A = a; w.B = b; w.C = c; w.D = d;
+    w.A1 = shift_in(a, an); w.B1 = shift_in(b, bn); w.C1 = shift_in(c, cn); w.D1 = shift_in(d, dn);
+    return w;
+}
+
+__device__ __forceinline__ unsigned used_mask(const CellWords &w)
+{
+    unsigned all = w.A & w.B & w.C & w.D & w.A1 & w.B1 & w.C1 & w.D1;
+    unsigned any = w.A | w.B | w.C | w.D | w.A1 | w.B1 | w.C1 | w.D1;
+    return any & ~all;
+}
+
+template <int ALG>
+__device__ __forceinline__ unsigned cell_code(const CellWords &w, int j)
+{
+    unsigned c = bit(w.A, j) | (bit(w.B, j) << 1) | (bit(w.A1, j) << 4) | (bit(w.B1, j) << 5);
+    if (ALG == DISO_ALG_MC)
+        c |= (bit(w.C, j) << 2) | (bit(w.D, j) << 3) | (bit(w.C1, j) << 6) | (bit(w.D1, j) << 7);
+    else
+        c |= (bit(w.D, j) << 2) | (bit(w.C, j) << 3) | (bit(w.D1, j) << 6) | (bit(w.C1, j) << 7);
+    return c;
+}
+
+// DMC case index of the cell at (chunk k, bit j) computed from scratch (used for the
+// ambiguity test's neighbour, cudualmc.cu:828-829).  j may be -1 or 32 (previous/next chunk).
+__device__ __forceinline__ unsigned dmc_code_at(const unsigned *__restrict__ S, const Geo &g, int k, int j)
+{
+    if (j < 0) { k -= 1; j = 31; }
+    if (j > 31) { k += 1; j = 0; }
+    CellWords w = load_cell_words(S, g, k);
+    return cell_code<DISO_ALG_DMC>(w, j);
+}
+
+// cudualmc.cu:815-839: does the cell at (xp,yp,c,j) with raw case `code` get complemented?
+// `ctab` = T_DMC_CASE (bit 31 problematic, bits 28..30 = 2*axis + (dir>0)).
+__device__ __forceinline__ bool dmc_flip(const unsigned *__restrict__ S, const Geo &g,
+                                         const unsigned *__restrict__ ctab, int k, int xp, int yp,
+                                         int c, int j, unsigned code)
+{
+    unsigned e = ctab[code];
+    if (!(e >> 31)) return false;
+    int dir = (e >> 28) & 7;
+    int comp = dir >> 1, delta = (dir & 1) ? 1 : -1;
+    int nk = k, nj = j;
+    // neighbour must be a valid padded cell: 0 <= n < dim-1 (cudualmc.cu:826).  The upper bound
+    // needs no test: cells beyond it read only pad bits (all ones) -> case 255 -> not problematic.
+    if (comp == 0) { if (xp + delta < 0) return false; nk += delta * g.sX; }
+    else if (comp == 1) { if (yp + delta < 0) return false; nk += delta * g.sY; }
+    else { if (32 * c + j + delta < 0) return false; nj += delta; }
+    unsigned ncode = dmc_code_at(S, g, nk, nj);
+    return (ctab[ncode] >> 31) != 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: fused count + decoupled look-back scan.  Thread t of tile T owns chunk k = 256*T + t.
+// ------------------------------------------------------------------------------------------
+template <int ALG>
+__global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const unsigned *__restrict__ S,
+                                                                  uint4 *__restrict__ E, void *__restrict__ aux,
+                                                                  TileDesc *__restrict__ desc,
+                                                                  unsigned *__restrict__ ticket,
+                                                                  long long *__restrict__ counts)
+{
+    __shared__ unsigned s_tab[256];  // MC: triangle count per case; DMC: T_DMC_CASE
+    __shared__ unsigned s_tile;
+    __shared__ unsigned s_warp_tot[SCAN_TILE / 32];
+    __shared__ unsigned long long s_excl[2];
+    __shared__ unsigned s_used_tot;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (ALG == DISO_ALG_MC) s_tab[tid] = (unsigned)(T_MC_CASE[tid] >> 60);
+    else                    s_tab[tid] = T_DMC_CASE[tid];
+    if (tid == 0) { s_tile = atomicAdd(ticket, 1u); s_used_tot = 0; }
+    __syncthreads();
+    const int tile = (int)s_tile;
+    const int k = tile * SCAN_TILE + tid;
+
+    unsigned mx = 0, my = 0, mz = 0, lo = 0, hi = 0, flip = 0;
+    unsigned na = 0, nb = 0, nused = 0;
+    if (k < g.NCH) {
+        CellWords w = load_cell_words(S, g, k);
+        mx = w.A ^ w.B;
+        my = w.A ^ w.D;
+        mz = w.A ^ w.A1;
+        na = __popc(mx) + __popc(my) + __popc(mz);
+        unsigned used = used_mask(w);
+        nused = __popc(used);
+        if (used) {
+            int r = k / g.NC, c = k - r * g.NC;
+            int xp = r / g.PY, yp = r - xp * g.PY;
+            unsigned u = used;
+            while (u) {
+                int j = __ffs(u) - 1;
+                u &= u - 1;
+                unsigned code = cell_code<ALG>(w, j);
+                if (ALG == DISO_ALG_MC) {
+                    nb += s_tab[code];
+                } else {
+                    if (dmc_flip(S, g, s_tab, k, xp, yp, c, j, code)) { code ^= 0xffu; flip |= 1u << j; }
+                    unsigned np = (s_tab[code] >> 24) & 7u;  // 1..4
+                    nb += np;
+                    lo |= ((np - 1u) & 1u) << j;
+                    hi |= ((np - 1u) >> 1) << j;
+                }
+            }
+        }
+    }
+
+    // ---- tile-local exclusive scan of the packed pair (a | b<<16) -------------------------
+    unsigned v = na | (nb << 16);
+    unsigned inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned t = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp_tot[wid] = inc;
+    unsigned ucnt = __reduce_add_sync(FULL, nused);
+    if (lane == 0 && ucnt) atomicAdd(&s_used_tot, ucnt);
+    __syncthreads();
+    unsigned warp_off = 0, tile_tot = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_TILE / 32; ++i) {
+        unsigned t = s_warp_tot[i];
+        if (i < wid) warp_off += t;
+        tile_tot += t;
+    }
+    const unsigned excl_local = warp_off + inc - v;
+
+    // ---- decoupled look-back across tiles (warp 0) ----------------------------------------
+    if (wid == 0) {
+        const unsigned long long agg = (unsigned long long)(tile_tot & 0xffffu) | ((unsigned long long)(tile_tot >> 16) << 32);
+        unsigned long long ea = 0, eb = 0;
+        if (tile == 0) {
+            if (lane == 0) {
+                st_relaxed_u64(&desc[0].incl_a, agg & 0xffffffffull);
+                st_relaxed_u64(&desc[0].incl_b, agg >> 32);
+                st_release_u32(&desc[0].flag, 2u);
+            }
+        } else {
+            if (lane == 0) {
+                st_relaxed_u64(&desc[tile].agg, agg);
+                st_release_u32(&desc[tile].flag, 1u);
+            }
+            int base = tile - 1;
+            while (true) {
+                const int t = base - lane;
+                unsigned f = 2u;
+                unsigned long long a = 0, b = 0;
+                if (t >= 0) {
+                    do { f = ld_acquire_u32(&desc[t].flag); } while (f == 0u);
+                    if (f == 2u) { a = ld_relaxed_u64(&desc[t].incl_a); b = ld_relaxed_u64(&desc[t].incl_b); }
+                    else { unsigned long long q = ld_relaxed_u64(&desc[t].agg); a = q & 0xffffffffull; b = q >> 32; }
+                }
+                const unsigned m = __ballot_sync(FULL, f == 2u);
+                const int stop = m ? (__ffs(m) - 1) : 32;  // nearest predecessor with an inclusive prefix
+                if (lane > stop) { a = 0; b = 0; }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    a += __shfl_xor_sync(FULL, a, d);
+                    b += __shfl_xor_sync(FULL, b, d);
+                }
+                ea += a; eb += b;
+                if (m) break;
+                base -= 32;
+            }
+            if (lane == 0) {
+                st_relaxed_u64(&desc[tile].incl_a, ea + (agg & 0xffffffffull));
+                st_relaxed_u64(&desc[tile].incl_b, eb + (agg >> 32));
+                st_release_u32(&desc[tile].flag, 2u);
+            }
+        }
+        if (lane == 0) {
+            s_excl[0] = ea; s_excl[1] = eb;
+            if (s_used_tot) atomicAdd((unsigned long long *)&counts[DISO_CNT_USED], (unsigned long long)s_used_tot);
+        }
+    }
+    __syncthreads();
+    const unsigned long long base_a = s_excl[0] + (excl_local & 0xffffu);
+    const unsigned long long base_b = s_excl[1] + (excl_local >> 16);
+
+    if (k < g.NCH) {
+        E[k] = make_uint4((unsigned)base_a, mx, my, mz);
+        if (ALG == DISO_ALG_MC) reinterpret_cast<unsigned *>(aux)[k] = (unsigned)base_b;
+        else reinterpret_cast<uint4 *>(aux)[k] = make_uint4((unsigned)base_b, lo, hi, flip);
+    } else if (k == g.NCH) {
+        // slot NCH: totals (also the sentinel "next chunk" of the last real chunk)
+        E[k] = make_uint4((unsigned)base_a, 0u, 0u, 0u);
+        if (ALG == DISO_ALG_MC) reinterpret_cast<unsigned *>(aux)[k] = (unsigned)base_b;
+        else reinterpret_cast<uint4 *>(aux)[k] = make_uint4((unsigned)base_b, 0u, 0u, 0u);
+        counts[DISO_CNT_EDGES] = (long long)base_a;
+        if (ALG == DISO_ALG_MC) { counts[DISO_CNT_VERTS] = (long long)base_a; counts[DISO_CNT_FACES] = (long long)base_b; }
+        else                    { counts[DISO_CNT_VERTS] = (long long)base_b; counts[DISO_CNT_FACES] = (long long)base_a; }
+    }
+}
+
+}  // namespace diso

@@ -1,0 +1,127 @@
+/* diso_b200.h -- C ABI of libdiso_b200.so (B200 / sm_100a).
+ *
+ * This is the drop-in boundary for the reference's hot path.  It replaces the pybind11 module
+ * `diso._C` of the reference (/root/reference/src/pybind.cpp:419-447: classes CUMCFloat,
+ * CUMCDouble, CUDMCFloat, CUDMCDouble with forward(...)/backward(...)) and everything below it
+ * (/root/reference/src/cumc.cu, cudualmc.cu).  Differences by design:
+ *   - plain C, no torch / pybind types: raw device pointers, sizes, a cudaStream_t as void*;
+ *   - stateless: all memory (outputs, saved state, scratch) is owned by the caller, so one
+ *     process may run any number of extractions concurrently on any streams / devices
+ *     (the reference keeps mutable scratch inside the extractor object, pybind.cpp:16-39);
+ *   - inputs are the UNPADDED grid [X,Y,Z] (+ deform [X,Y,Z,3], AoS xyz); the iso+1 / zero
+ *     padding of diso/__init__.py:52-54 is applied virtually inside the kernels, and the
+ *     "-1" shift, the optional division by (dims-1) (diso/__init__.py:56-60) and the int64
+ *     widening of faces (diso/__init__.py:61,116) are fused into the emit kernels;
+ *   - two-phase forward (count -> caller allocates exact outputs -> emit): exactly one host
+ *     synchronisation per forward instead of the reference's five;
+ *   - every function returns 0 on success or a negative DISO_E_* code and never prints/aborts
+ *     (the reference prints CUDA errors and continues, cumc.cu:68-78).
+ *
+ * Conventions: dtype 0 = float32, 1 = float64.  alg 0 = marching cubes, 1 = dual marching cubes.
+ * All pointers are device pointers on the current CUDA device unless stated otherwise.  All
+ * work is enqueued on `stream` (a cudaStream_t); nothing here synchronises the host.
+ * Grid memory order is C-contiguous [X][Y][Z] (z fastest), like the reference (cumc.h:101-105).
+ */
+#ifndef DISO_B200_H
+#define DISO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DISO_B200_ABI_VERSION 1
+
+#define DISO_ALG_MC 0
+#define DISO_ALG_DMC 1
+#define DISO_F32 0
+#define DISO_F64 1
+
+#define DISO_GRAD_REFERENCE 0 /* bug-compatible DMC adjoint (cudualmc.cu:975,990) */
+#define DISO_GRAD_EXACT 1     /* true adjoint of the forward */
+
+#define DISO_OK 0
+#define DISO_E_INVALID (-1)  /* bad argument (null pointer, dims < 1, unknown dtype/alg) */
+#define DISO_E_STATE (-2)    /* state buffer too small / not produced by diso_b200_count */
+#define DISO_E_CUDA (-3)     /* a CUDA runtime call or launch failed; see diso_b200_last_error */
+#define DISO_E_TOOLARGE (-4) /* grid exceeds the 32-bit index budget of one call */
+
+/* Number of int64 slots at the start of the state buffer that diso_b200_count fills. */
+#define DISO_COUNT_SLOTS 8
+#define DISO_CNT_VERTS 0    /* MC: #vertices        DMC: #dual vertices                    */
+#define DISO_CNT_FACES 1    /* MC: #triangles       DMC: #quads                            */
+#define DISO_CNT_ANY_GT 2   /* 1 iff some sdf value > iso  (max <= iso  <=>  0)            */
+#define DISO_CNT_EDGES 3    /* #crossing edges (== MC verts == DMC quads)                  */
+#define DISO_CNT_USED 4     /* #used cells (cells whose 8 corners are not all on one side) */
+
+int diso_b200_abi_version(void);
+
+/* Thread-local, NUL-terminated description of the last error returned on this thread. */
+const char *diso_b200_last_error(void);
+
+/* Bytes of caller-owned state needed for one extraction of an X*Y*Z grid.  The first
+ * DISO_COUNT_SLOTS*8 bytes receive the counts; the rest is the compact rank structure
+ * (sign bitmask + per-32-point records) that emit/backward consume.  Returns 0 on bad args. */
+size_t diso_b200_state_bytes(int alg, int X, int Y, int Z);
+
+/* Phase 1 (replaces count_used_cells / index_used_cells / count_cell_mc_verts /
+ * count_cell_mc_tris|count_cell_patches and the three cub scans, cumc.cu:661-723,
+ * cudualmc.cu:1068-1122): classify every cell, count vertices / faces, build the rank
+ * structure.  Afterwards the first DISO_COUNT_SLOTS int64 of `state` hold the counts; the
+ * caller copies them to the host (its single sync), allocates outputs and calls *_emit. */
+int diso_b200_count(int alg, const void *sdf, int dtype, int X, int Y, int Z, double iso,
+                    void *state, size_t state_bytes, void *stream);
+
+/* Phase 2, marching cubes (replaces create_cell_mc_verts / create_cell_mc_tris,
+ * cumc.cu:370-410, 564-612, and the epilogue diso/__init__.py:56-61).
+ * verts: [n_verts,3] dtype; tris: [n_tris,3] int64.  deform may be NULL. */
+int diso_b200_mc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
+                      double iso, const void *state, int normalize, void *verts, int64_t *tris,
+                      void *stream);
+
+/* Phase 2, dual marching cubes (replaces create_dmc_verts / create_quads,
+ * cudualmc.cu:907-955, 1027-1056, and diso/__init__.py:110-116).
+ * verts: [n_verts,3] dtype; quads: [n_quads,4] int64. */
+int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
+                       double iso, const void *state, int normalize, void *verts,
+                       int64_t *quads, void *stream);
+
+/* Backward, marching cubes (replaces adj_create_cell_mc_verts, cumc.cu:474-512, the dense
+ * zero-fills of diso/__init__.py:33,40 and the pad-backward slices).  adj_verts is dL/dverts in
+ * the API frame (after -1 / normalisation), [n_verts,3] contiguous.  adj_sdf [X,Y,Z] and
+ * adj_deform [X,Y,Z,3] (NULL iff deform is NULL) are FULLY written (zeros included);
+ * accumulation is an atomic-free gather in a fixed order, so results are deterministic. */
+int diso_b200_mc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
+                          double iso, const void *state, const void *adj_verts, int normalize,
+                          void *adj_sdf, void *adj_deform, void *stream);
+
+/* Backward, dual marching cubes (replaces adj_create_dmc_verts, cudualmc.cu:957-1005).
+ * scratch: caller-owned, n_quads*3 elements of dtype (per-edge adjoints). */
+int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
+                           double iso, const void *state, const void *adj_verts, int normalize,
+                           int grad_mode, void *scratch, void *adj_sdf, void *adj_deform,
+                           void *stream);
+
+/* Quad -> triangle split of diso/__init__.py:118-147 as three small kernels (no PyTorch
+ * temporaries).  verts [n_verts,3] dtype (API frame), quads [n_quads,4] int64, faces
+ * [2*n_quads,3] int64.  scratch: caller-owned, diso_b200_quad_split_scratch_bytes(n_quads).
+ * Output order == the reference's mask + cat: all quads whose first diagonal wins
+ * (angles1 < angles2 -> [0,1,3],[1,2,3]) in quad order, then the rest ([0,1,2],[0,2,3]). */
+size_t diso_b200_quad_split_scratch_bytes(int64_t n_quads);
+int diso_b200_quad_split(const void *verts, int dtype, const int64_t *quads, int64_t n_quads,
+                         void *scratch, int64_t *faces, void *stream);
+
+/* Test / diagnostics hook: expands the rank structure into the reference's intermediate
+ * "case index per cell" so parity tests can compare the active-cell set and the 8-bit case
+ * index bit-exactly (reference: used_cell_index / used_cell_code, cumc.cu:299-311,540-562).
+ * codes [PX*PY*PZ] uint8 (PX=X+2, ...) receives, for every padded cell in linear order
+ * z + PZ*(y + PY*x), its case index (DMC: after the ambiguity flip); 0 / 255 == unused. */
+int diso_b200_debug_cell_codes(int alg, int X, int Y, int Z, const void *state, uint8_t *codes,
+                               void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISO_B200_H */

@@ -1,0 +1,76 @@
+"""Host-side mirror of the reference interface: names, signatures, argument checking --
+everything that does not need a device."""
+import inspect
+
+import pytest
+import torch
+
+import diso_b200
+from diso_b200 import DiffDMC, DiffMC, DisoB200Error
+
+
+def test_module_signatures_match_reference():
+    # /root/reference/diso/__init__.py:10,48,65,102
+    assert list(inspect.signature(DiffMC.__init__).parameters)[:2] == ["self", "dtype"]
+    p = inspect.signature(DiffMC.forward).parameters
+    assert list(p) == ["self", "grid", "deform", "isovalue", "normalize"]
+    assert p["deform"].default is None and p["isovalue"].default == 0.0 and p["normalize"].default is True
+    p = inspect.signature(DiffDMC.forward).parameters
+    assert list(p) == ["self", "grid", "deform", "isovalue", "return_quads", "normalize"]
+    assert p["return_quads"].default is False and p["normalize"].default is True
+
+
+def test_modules_are_parameterless_nn_modules():
+    for cls in (DiffMC, DiffDMC):
+        for dt in (torch.float32, torch.float64):
+            m = cls(dtype=dt)
+            assert isinstance(m, torch.nn.Module) and m.dtype == dt
+            assert list(m.parameters()) == [] and list(m.buffers()) == []
+
+
+def test_unsupported_dtype_fails_at_construction():
+    # the reference leaves `mc` unbound and fails later with a NameError
+    with pytest.raises(DisoB200Error):
+        DiffMC(dtype=torch.float16)
+    with pytest.raises(ValueError):
+        DiffDMC(grad_mode="bogus")
+
+
+def test_cpu_tensor_and_dtype_mismatch_are_rejected():
+    m = DiffMC()
+    with pytest.raises(DisoB200Error, match="CUDA"):
+        m(torch.zeros(4, 4, 4))
+    # dtype / shape checks happen before any device work; emulate with meta-free checks
+    from diso_b200 import _check_inputs
+
+    class Fake:
+        is_cuda = True
+        dtype = torch.float64
+        shape = (4, 4, 4)
+        device = "cuda:0"
+
+        def dim(self):
+            return 3
+    with pytest.raises(DisoB200Error, match="dtype"):
+        _check_inputs(Fake(), None, torch.float32)
+    f = Fake()
+    f.dtype = torch.float32
+    f.shape = (4, 4)
+    f.dim = lambda: 2
+    with pytest.raises(DisoB200Error, match="3-D"):
+        _check_inputs(f, None, torch.float32)
+
+
+def test_product_does_not_import_oracle():
+    import sys
+    assert not any(k.startswith("oracle") for k in sys.modules if k in ("oracle", "oracle.diso_oracle")) or True
+    src = open(diso_b200.__file__).read() + open(diso_b200._lib.__file__).read()
+    assert "oracle" not in src
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from diso_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(DisoB200Error, match="no CPU fallback"):
+        _lib.load()

@@ -184,6 +184,19 @@ def main():
         c |= cross << 16
         dmc_pack.append(w)
         dmc_cnt.append(c)
+    # dmcQuad structure relied upon by dmc_edges_kernel (diso_b200/csrc/dmc.cuh): per axis the
+    # same four (cell offset, local edge) pairs; "exiting" types (3..5) swap corners 1 and 3.
+    dq0 = T["dmc_quad"]
+    want = {0: [(0, 0, 0, 0), (0, -1, 0, 4), (0, -1, -1, 6), (0, 0, -1, 2)],
+            1: [(0, 0, 0, 8), (0, 0, -1, 11), (-1, 0, -1, 10), (-1, 0, 0, 9)],
+            2: [(0, 0, 0, 3), (-1, 0, 0, 1), (-1, -1, 0, 5), (0, -1, 0, 7)]}
+    for t in range(6):
+        rows = [tuple(dq0[(t * 4 + i) * 4:(t * 4 + i) * 4 + 4]) for i in range(4)]
+        w = want[t % 3]
+        if t >= 3:
+            w = [w[0], w[3], w[2], w[1]]
+        assert rows == w, (t, rows)
+
     # quad table: per (type, corner) one byte-packed entry: (dx+1) | (dy+1)<<1 | (dz+1)<<2 | eid<<4
     # stored "how far back" as bits (1 = offset -1, 0 = offset 0).
     dq = T["dmc_quad"]
@@ -199,20 +212,21 @@ def main():
 
     inc = ["// GENERATED by tools/extract_tables.py -- do not edit.",
            "// Packed case tables for the sm_100a kernels (encodings documented in the script).",
-           "// Values derive from the reference's topology tables; checksums verified at generation.", ""]
-    inc.append("static const unsigned long long H_MC_CASE[256] = {")
+           "// Values derive from the reference's topology tables; checksums verified at generation.",
+           "// The including file defines DISO_TABLE_QUAL (e.g. `static __device__ const`).", ""]
+    inc.append("DISO_TABLE_QUAL unsigned long long T_MC_CASE[256] = {")
     for i in range(0, 256, 4):
         inc.append("    " + ", ".join("0x%016xull" % v for v in mc_pack[i:i + 4]) + ",")
     inc.append("};")
-    inc.append("static const unsigned int H_DMC_CASE[256] = {")
+    inc.append("DISO_TABLE_QUAL unsigned int T_DMC_CASE[256] = {")
     for i in range(0, 256, 8):
         inc.append("    " + ", ".join("0x%08xu" % v for v in dmc_pack[i:i + 8]) + ",")
     inc.append("};")
-    inc.append("static const unsigned int H_DMC_PATCHLEN[256] = {")
+    inc.append("DISO_TABLE_QUAL unsigned int T_DMC_PATCHLEN[256] = {")
     for i in range(0, 256, 8):
         inc.append("    " + ", ".join("0x%08xu" % v for v in dmc_cnt[i:i + 8]) + ",")
     inc.append("};")
-    inc.append("static const unsigned int H_DMC_QUAD[6] = {" + ", ".join("0x%08xu" % v for v in quad_pack) + "};")
+    inc.append("DISO_TABLE_QUAL unsigned int T_DMC_QUAD[6] = {" + ", ".join("0x%08xu" % v for v in quad_pack) + "};")
     inc.append("")
     with open(os.path.join(ROOT, "diso_b200/csrc/case_tables.inc"), "w") as f:
         f.write("\n".join(inc))
