@@ -1,0 +1,411 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the hot path (BASELINE.json: Gvoxel/s, forward+backward,
+DiffMC and DiffDMC, 512^3 random-init SDF with learnable deform, fp32; % of HBM roofline).
+
+One "step" = DiffMC forward+backward AND DiffDMC (return_quads=True) forward+backward on one
+512^3 grid, with the harness of BASELINE.md section 2:
+    verts, faces = m(sdf, deform); (verts * w).sum().backward()        (w fixed, random)
+`value` counts G = X*Y*Z voxels per extractor pass (2*G per step) over the device-timed region
+with inputs resident in HBM; `e2e` is the same step starting from pinned HOST buffers (H2D of sdf
+and deform every step, D2H of the two losses).  Multi-GPU: one independent 512^3 shape per rank
+(config C5a, seeds differ per rank), no data-path collective -> weak scaling.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size 512] [--kind flexi]
+
+`--impl reference`: the reference has NO CPU path and cannot be compiled for the
+CPU, so this arm times the CPU oracle port (oracle/, a restatement of the reference algorithm) on
+all host cores over a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Gvoxels/s fwd+bwd DiffMC+DiffDMC 512^3 rand SDF"
+UNIT = "Gvoxel/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--kind", default="flexi", choices=["flexi", "sparse", "dense"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference CUDA build beside ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks line"), runs during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        return False
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        busy = sm[len(sm) // 2:] if sm else []  # upper half ~= samples under load
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic bytes (BASELINE.md section 3 / DESIGN.md section 5)
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(G, s, V, F, k, E, deform, w=8):
+    fwd = G * s + 3 * V * s + k * F * w + (3 * min(E, G) * s if deform else 0)
+    bwd = 3 * V * s + min(E, G) * s + G * s + ((3 * min(E, G) * s + 3 * G * s) if deform else 0)
+    return fwd, bwd
+
+
+def kernel_bytes(name, G, s, c_mc, c_dmc, deform):
+    """Share of the algorithmic bytes each kernel is responsible for."""
+    Vm, Fm, Em = c_mc["verts"], c_mc["faces"], c_mc["endpoints"]
+    Vd, Qd = c_dmc["verts"], c_dmc["faces"]
+    d3 = 3 if deform else 0
+    table = {
+        "sign_pack_f32x4": G * s, "sign_pack": G * s,
+        "classify_scan_mc": 0, "classify_scan_dmc": 0,
+        "mc_emit_verts": 3 * Vm * s + d3 * min(Em, G) * s,
+        "mc_emit_tris": 3 * Fm * 8,
+        "mc_backward": 3 * Vm * s + min(Em, G) * s + G * s + d3 * (min(Em, G) + G) * s,
+        "dmc_emit_verts": 3 * Vd * s + d3 * min(Em, G) * s,
+        "dmc_emit_quads": 4 * Qd * 8,
+        "dmc_edge_adjoint": 3 * Vd * s,
+    }
+    return table.get(name, 0)
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline leg and --impl reference)
+# ------------------------------------------------------------------------------------------------
+def oracle_pass(sdf, deform):
+    """MC + DMC forward+backward on one numpy sample with the CPU oracle. Returns voxels processed."""
+    import numpy as np
+    from oracle import diso_oracle as O
+    for alg in ("mc", "dmc"):
+        v, _ = O.forward(alg, sdf, deform, 0.0, True)
+        w = np.ones_like(v)
+        O.backward(alg, sdf, deform, 0.0, True, w, "reference")
+    return 2 * sdf.size
+
+
+def cpu_sample(kind, n, seed, dtype):
+    from diso_b200 import synthetic as syn
+    import torch
+    dt = torch.float32 if dtype == "f32" else torch.float64
+    return syn.random_sdf(n, kind, seed, dt).numpy(), syn.random_deform(n, seed + 1, dt).numpy()
+
+
+def run_reference_arm(args, rank, world):
+    """CPU oracle port on all host cores; bounded sample per step (see module docstring)."""
+    if rank != 0:
+        return
+    from oracle import diso_oracle as O
+    O.lib()
+    cores = os.cpu_count() or 1
+    n = 64
+    samples = [cpu_sample(args.kind, n, 100 + i, args.dtype) for i in range(cores)]
+
+    def step():
+        out = [0] * cores
+
+        def work(i):
+            out[i] = oracle_pass(*samples[i])  # ctypes releases the GIL inside the C oracle
+        th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        return sum(out)
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    t0 = time.perf_counter()
+    vox = 0
+    for _ in range(args.steps):
+        vox += step()
+    dt = time.perf_counter() - t0
+    value = vox / dt / 1e9
+    sample = "%d concurrent %d^3 crops of the rand-%s workload per step (one per host thread), MC+DMC fwd+bwd each" % (cores, n, args.kind)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "C4: random-init %d^3 SDF (rand-%s) + learnable deform, DiffMC and DiffDMC fwd+bwd" % (args.size, args.kind),
+                       "note": "reference has no CPU path; timed: CPU oracle port on a bounded sample"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import diso_b200
+    from diso_b200 import _lib, synthetic as syn
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dt = torch.float32 if args.dtype == "f32" else torch.float64
+    s_bytes = 4 if args.dtype == "f32" else 8
+    n = args.size
+    G = n ** 3
+
+    # C5a: one independent shape per rank (seeds differ), generated on the CPU, pinned for the e2e leg
+    sdf_h = syn.random_sdf(n, args.kind, seed=rank, dtype=dt).pin_memory()
+    def_h = syn.random_deform(n, seed=1000 + rank, dtype=dt).pin_memory()
+    sdf_d = sdf_h.to(dev).requires_grad_(True)
+    def_d = def_h.to(dev).requires_grad_(True)
+    mods = {"mc": (diso_b200.DiffMC(dt), {}), "dmc": (diso_b200.DiffDMC(dt), dict(return_quads=True))}
+
+    # fixed random dL/dverts per extractor (sizes are deterministic for a fixed input)
+    wts, counts = {}, {}
+    with torch.no_grad():
+        for key, (m, kw) in mods.items():
+            v, f = m(sdf_d, def_d, **kw)
+            gen = torch.Generator(device="cpu").manual_seed(7)
+            wts[key] = torch.rand(v.shape, generator=gen, dtype=torch.float32).to(dt).to(dev)
+            c = diso_b200.extract_counts(key, sdf_d.detach())
+            counts[key] = dict(verts=v.shape[0], faces=f.shape[0], edges=c["edges"])
+            del v, f
+    # E = grid points incident to >= 1 crossing edge (for the algorithmic-bytes formula)
+    with torch.no_grad():
+        b = sdf_d.detach() >= 0
+        bp = torch.nn.functional.pad(b, (1, 1, 1, 1, 1, 1), value=True)
+        inc = torch.zeros_like(bp)
+        for ax in range(3):
+            a0 = bp.narrow(ax, 0, bp.shape[ax] - 1)
+            a1 = bp.narrow(ax, 1, bp.shape[ax] - 1)
+            cr = a0 != a1
+            inc.narrow(ax, 0, bp.shape[ax] - 1).logical_or_(cr)
+            inc.narrow(ax, 1, bp.shape[ax] - 1).logical_or_(cr)
+        endpoints = int(inc[1:-1, 1:-1, 1:-1].sum().item())
+        del b, bp, inc, a0, a1, cr
+    for key in counts:
+        counts[key]["endpoints"] = endpoints
+    torch.cuda.empty_cache()
+
+    def step(s, d):
+        losses = []
+        for key, (m, kw) in mods.items():
+            s.grad = None
+            d.grad = None
+            v, f = m(s, d, **kw)
+            loss = (v * wts[key]).sum()
+            loss.backward()
+            losses.append(loss)
+        return losses
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step(sdf_d, def_d)
+    sync_all()
+    L0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk, _lib.kernel_profile() as prof:
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            step(sdf_d, def_d)
+        e1.record()
+        sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - L0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    # ---- end-to-end timing: pinned host inputs -> device every step, loss read back -------------
+    def e2e_step():
+        s = sdf_h.to(dev, non_blocking=True).requires_grad_(True)
+        d = def_h.to(dev, non_blocking=True).requires_grad_(True)
+        return [float(x.item()) for x in step(s, d)]
+    e2e_step()
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(2, min(args.steps, 5))
+    e2.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e3.record()
+    sync_all()
+    t = torch.tensor([e2.elapsed_time(e3)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / e2e_steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel roofline (dominant kernel, live CUDA-event durations of the timed region) ----
+    per_kernel = {k: sum(v) / len(v) for k, v in prof.times.items()}
+    total_k = {k: sum(v) / args.steps for k, v in prof.times.items()}
+    dom = max(total_k, key=total_k.get)
+    peak, peak_src = peak_hbm()
+    kb = kernel_bytes(dom, G, s_bytes, counts["mc"], counts["dmc"], True)
+    achieved = kb / (per_kernel[dom] * 1e-3) / 1e9
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get("%s@%d^3-%s-%s" % (dom, n, args.kind, args.dtype))
+    except Exception:
+        pass
+    fwd_mc, bwd_mc = algorithmic_bytes(G, s_bytes, counts["mc"]["verts"], counts["mc"]["faces"], 3, endpoints, True)
+    fwd_d, bwd_d = algorithmic_bytes(G, s_bytes, counts["dmc"]["verts"], counts["dmc"]["faces"], 4, endpoints, True)
+    step_bytes = fwd_mc + bwd_mc + fwd_d + bwd_d
+    ms_step = ms_max / args.steps
+    kernels = {}
+    for k in sorted(total_k, key=total_k.get, reverse=True):
+        b_ = kernel_bytes(k, G, s_bytes, counts["mc"], counts["dmc"], True)
+        kernels[k] = {"ms": round(per_kernel[k], 4), "share_of_step": round(total_k[k] / ms_step, 4),
+                      "alg_GBps": round(b_ / (per_kernel[k] * 1e-3) / 1e9, 1) if b_ else None}
+
+    line = {
+        "metric": METRIC, "value": world * 2 * G / (ms_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": "C4: random-init %d^3 SDF (rand-%s, seed=rank) + learnable deform, DiffMC and DiffDMC(return_quads) fwd+bwd per step" % (n, args.kind),
+                   "grid": [n, n, n], "l2": "inputs (%.2f GB) exceed the 126 MB L2" % ((G * s_bytes * 4) / 1e9),
+                   "parallelism": "one independent shape per GPU (C5a), no collective"},
+        "clocks": clk.summary(),
+        "e2e": {"value": world * 2 * G / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(sdf_h.numel() * s_bytes + def_h.numel() * s_bytes), "d2h_bytes_per_step": 2 * s_bytes},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel_ms": per_kernel[dom], "kernel_alg_bytes": kb},
+        "step_roofline": {"alg_bytes_per_step": step_bytes, "achieved_GBps": step_bytes / (ms_step * 1e-3) / 1e9,
+                          "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
+        "kernels": kernels,
+        "mesh": {"mc": counts["mc"], "dmc": counts["dmc"]},
+    }
+
+    # ---- CPU baseline (rank 0, N=1): single-threaded oracle port on a bounded sample --------------
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            ncpu = 128
+            smp = cpu_sample(args.kind, ncpu, 0, args.dtype)
+            t0 = time.perf_counter()
+            vox = oracle_pass(*smp)
+            dtc = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": vox / dtc / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "host_cores": os.cpu_count(),
+                                    "sample": "%d^3 crop of the rand-%s workload with deform, MC+DMC fwd+bwd, %.1f s" % (ncpu, args.kind, dtc)}
+        except Exception as ex:  # the baseline is a reported number, never a dependency
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "failed: %s" % ex}
+
+    # ---- reference CUDA build on the same GPU, same harness (reported beside ours; N=1 only) ------
+    if world == 1 and not args.no_ref_cuda:
+        try:
+            from tests.refload import load_reference
+            ref = load_reference()
+            if ref is None:
+                line["ref_cuda"] = {"unavailable": "baseline/_ref not present"}
+            else:
+                rmods = {"mc": (ref.DiffMC(dt), {}), "dmc": (ref.DiffDMC(dt), dict(return_quads=True))}
+
+                def rstep():
+                    for key, (m, kw) in rmods.items():
+                        sdf_d.grad = None
+                        def_d.grad = None
+                        v, f = m(sdf_d, def_d, **kw)
+                        (v * wts[key]).sum().backward()
+                for _ in range(2):
+                    rstep()
+                torch.cuda.synchronize()
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                nref = 3
+                r0.record()
+                for _ in range(nref):
+                    rstep()
+                r1.record()
+                torch.cuda.synchronize()
+                rms = r0.elapsed_time(r1) / nref
+                line["ref_cuda"] = {"ms_per_step": rms, "value": 2 * G / (rms * 1e-3) / 1e9, "unit": UNIT,
+                                    "speedup_device": rms / ms_step,
+                                    "what": "unmodified SarahWeiii/diso v0.1.4 built for sm_100 (baseline/_ref), same inputs/harness"}
+        except Exception as ex:
+            line["ref_cuda"] = {"unavailable": "%s: %s" % (type(ex).__name__, ex)}
+
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,9 @@ SIGNATURES = {
     "diso_b200_quad_split_scratch_bytes": (_sz, [_i64]),
     "diso_b200_quad_split": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp]),
     "diso_b200_debug_cell_codes": (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
+    "diso_b200_launch_count": (ctypes.c_longlong, []),
+    "diso_b200_profile_enable": (_i, [_i]),
+    "diso_b200_profile_dump": (_i, [ctypes.c_char_p, _sz]),
 }
 
 _lib = None
@@ -62,3 +65,28 @@ def check(rc):
     if rc != 0:
         msg = load().diso_b200_last_error().decode("utf-8", "replace")
         raise DisoB200Error("libdiso_b200 error %d: %s" % (rc, msg))
+
+
+def launch_count():
+    return int(load().diso_b200_launch_count())
+
+
+class kernel_profile:
+    """Context manager: per-kernel device times (ms) of the library calls made inside it, measured
+    with CUDA events on the launching stream.  ``.times`` maps kernel name -> list of ms."""
+
+    def __enter__(self):
+        load().diso_b200_profile_enable(1)
+        self.times = {}
+        return self
+
+    def __exit__(self, *exc):
+        L = load()
+        buf = ctypes.create_string_buffer(1 << 20)
+        rc = L.diso_b200_profile_dump(buf, len(buf))
+        L.diso_b200_profile_enable(0)
+        check(rc)
+        for line in buf.value.decode().splitlines():
+            name, ms = line.rsplit(" ", 1)
+            self.times.setdefault(name, []).append(float(ms))
+        return False

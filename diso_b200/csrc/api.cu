@@ -3,6 +3,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "classify.cuh"
 #include "dmc.cuh"
@@ -81,6 +85,38 @@ template <typename T> Epilogue<T> make_epilogue(const Geo &g, int normalize)
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- tracing: launch counter + optional per-kernel CUDA-event timing (per host thread) --------
+std::atomic<long long> g_launches{0};
+struct ProfRec { const char *name; cudaEvent_t a, b; };
+std::atomic<bool> g_prof_on{false};  // process-wide: autograd runs backward on its own thread
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+
+template <typename F> int launch(const char *name, cudaStream_t st, F &&f)
+{
+    ProfRec r{name, nullptr, nullptr};
+    const bool prof = g_prof_on.load(std::memory_order_relaxed);
+    if (prof) {
+        CU_TRY(cudaEventCreate(&r.a));
+        CU_TRY(cudaEventCreate(&r.b));
+        CU_TRY(cudaEventRecord(r.a, st));
+    }
+    f();
+    if (prof) {
+        CU_TRY(cudaEventRecord(r.b, st));
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.push_back(r);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CU_LAUNCH_CHECK(name);
+    return DISO_OK;
+}
+#define LAUNCH(name, st, ...)                                   \
+    do {                                                        \
+        int rc_ = launch(name, st, [&]() { __VA_ARGS__; });     \
+        if (rc_) return rc_;                                    \
+    } while (0)
+
 // ---- phase 1 ---------------------------------------------------------------------------------
 template <typename T>
 int count_impl(int alg, const T *sdf, const Geo &g, double iso, const StateLayout &L, const StatePtrs &p, cudaStream_t st)
@@ -98,17 +134,15 @@ int count_impl(int alg, const T *sdf, const Geo &g, double iso, const StateLayou
     if (vec4) {
         const int NA = (g.Z + 31) / 32;
         const size_t smem = (size_t)warps * (NA + 2) * 4;
-        sign_pack_f32x4_kernel<<<cdiv(g.NR, warps), warps * 32, smem, st>>>(reinterpret_cast<const float *>(sdf), g,
-                                                                          (float)isoT, p.S, p.counts);
+        LAUNCH("sign_pack_f32x4", st, sign_pack_f32x4_kernel<<<cdiv(g.NR, warps), warps * 32, smem, st>>>(
+                                          reinterpret_cast<const float *>(sdf), g, (float)isoT, p.S, p.counts));
     } else {
-        sign_pack_kernel<T><<<cdiv(g.NR, warps), warps * 32, 0, st>>>(sdf, g, isoT, p.S, p.counts);
+        LAUNCH("sign_pack", st, sign_pack_kernel<T><<<cdiv(g.NR, warps), warps * 32, 0, st>>>(sdf, g, isoT, p.S, p.counts));
     }
-    CU_LAUNCH_CHECK("sign_pack");
     if (alg == DISO_ALG_MC)
-        classify_scan_kernel<DISO_ALG_MC><<<L.n_tiles, SCAN_TILE, 0, st>>>(g, p.S, p.E, p.aux, p.desc, p.ticket, p.counts);
+        LAUNCH("classify_scan_mc", st, classify_scan_kernel<DISO_ALG_MC><<<L.n_tiles, SCAN_TILE, 0, st>>>(g, p.S, p.E, p.aux, p.desc, p.ticket, p.counts));
     else
-        classify_scan_kernel<DISO_ALG_DMC><<<L.n_tiles, SCAN_TILE, 0, st>>>(g, p.S, p.E, p.aux, p.desc, p.ticket, p.counts);
-    CU_LAUNCH_CHECK("classify_scan");
+        LAUNCH("classify_scan_dmc", st, classify_scan_kernel<DISO_ALG_DMC><<<L.n_tiles, SCAN_TILE, 0, st>>>(g, p.S, p.E, p.aux, p.desc, p.ticket, p.counts));
     return DISO_OK;
 }
 
@@ -119,10 +153,9 @@ int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const 
     const int groups = cdiv(g.NCH, 32);
     const int grid = cdiv(groups, EMIT_WARPS);
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
-    mc_emit_verts_kernel<T><<<grid, EMIT_WARPS * 32, 0, st>>>(sdf, deform, g, isoT, padv, make_epilogue<T>(g, normalize), p.E, verts);
-    CU_LAUNCH_CHECK("mc_emit_verts");
-    mc_emit_tris_kernel<<<grid, EMIT_WARPS * 32, 0, st>>>(g, p.S, p.E, reinterpret_cast<const unsigned *>(p.aux), tris);
-    CU_LAUNCH_CHECK("mc_emit_tris");
+    const Epilogue<T> epi = make_epilogue<T>(g, normalize);
+    LAUNCH("mc_emit_verts", st, mc_emit_verts_kernel<T><<<grid, EMIT_WARPS * 32, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, verts));
+    LAUNCH("mc_emit_tris", st, mc_emit_tris_kernel<<<grid, EMIT_WARPS * 32, 0, st>>>(g, p.S, p.E, reinterpret_cast<const unsigned *>(p.aux), tris));
     return DISO_OK;
 }
 
@@ -134,10 +167,9 @@ int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const
     const int grid = cdiv(groups, EMIT_WARPS);
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
-    dmc_emit_verts_kernel<T><<<grid, EMIT_WARPS * 32, 0, st>>>(sdf, deform, g, isoT, padv, make_epilogue<T>(g, normalize), p.S, P, verts);
-    CU_LAUNCH_CHECK("dmc_emit_verts");
-    dmc_edges_kernel<T, 0><<<grid, EMIT_WARPS * 32, 0, st>>>(g, p.S, p.E, P, make_epilogue<T>(g, 0), nullptr, quads, nullptr);
-    CU_LAUNCH_CHECK("dmc_emit_quads");
+    const Epilogue<T> epi = make_epilogue<T>(g, normalize), epi0 = make_epilogue<T>(g, 0);
+    LAUNCH("dmc_emit_verts", st, dmc_emit_verts_kernel<T><<<grid, EMIT_WARPS * 32, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.S, P, verts));
+    LAUNCH("dmc_emit_quads", st, (dmc_edges_kernel<T, 0><<<grid, EMIT_WARPS * 32, 0, st>>>(g, p.S, p.E, P, epi0, nullptr, quads, nullptr)));
     return DISO_OK;
 }
 
@@ -146,9 +178,9 @@ int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, co
                      int normalize, T *adj_sdf, T *adj_deform, cudaStream_t st)
 {
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
-    mc_backward_kernel<T><<<cdiv(g.NCH, EMIT_WARPS), EMIT_WARPS * 32, 0, st>>>(sdf, deform, g, isoT, padv, make_epilogue<T>(g, normalize),
-                                                                             p.E, adj_verts, adj_sdf, adj_deform);
-    CU_LAUNCH_CHECK("mc_backward");
+    const Epilogue<T> epi = make_epilogue<T>(g, normalize);
+    LAUNCH("mc_backward", st, mc_backward_kernel<T><<<cdiv(g.NCH, EMIT_WARPS), EMIT_WARPS * 32, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E,
+                                                                                                      adj_verts, adj_sdf, adj_deform));
     return DISO_OK;
 }
 
@@ -159,11 +191,11 @@ int dmc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, c
     const int groups = cdiv(g.NCH, 32);
     const int grid = cdiv(groups, EMIT_WARPS);
     const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
+    const Epilogue<T> epi = make_epilogue<T>(g, normalize);
     if (grad_mode == DISO_GRAD_EXACT)
-        dmc_edges_kernel<T, 1><<<grid, EMIT_WARPS * 32, 0, st>>>(g, p.S, p.E, P, make_epilogue<T>(g, normalize), adj_verts, nullptr, scratch);
+        LAUNCH("dmc_edge_adjoint", st, (dmc_edges_kernel<T, 1><<<grid, EMIT_WARPS * 32, 0, st>>>(g, p.S, p.E, P, epi, adj_verts, nullptr, scratch)));
     else
-        dmc_edges_kernel<T, 2><<<grid, EMIT_WARPS * 32, 0, st>>>(g, p.S, p.E, P, make_epilogue<T>(g, normalize), adj_verts, nullptr, scratch);
-    CU_LAUNCH_CHECK("dmc_edge_adjoint");
+        LAUNCH("dmc_edge_adjoint", st, (dmc_edges_kernel<T, 2><<<grid, EMIT_WARPS * 32, 0, st>>>(g, p.S, p.E, P, epi, adj_verts, nullptr, scratch)));
     return mc_backward_impl<T>(sdf, deform, g, iso, p, scratch, 0, adj_sdf, adj_deform, st);
 }
 
@@ -174,6 +206,40 @@ extern "C" {
 int diso_b200_abi_version(void) { return DISO_B200_ABI_VERSION; }
 
 const char *diso_b200_last_error(void) { return g_err; }
+
+long long diso_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int diso_b200_profile_enable(int on)
+{
+    g_prof_on.store(on != 0);
+    if (!on) {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        for (auto &r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        g_prof.clear();
+    }
+    return DISO_OK;
+}
+
+int diso_b200_profile_dump(char *buf, size_t cap)
+{
+    if (!buf || cap == 0) return fail(DISO_E_INVALID, "null buffer");
+    std::string out;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto &r : g_prof) {
+        CU_TRY(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+        char line[128];
+        snprintf(line, sizeof(line), "%s %.6f\n", r.name, ms);
+        out += line;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    if (out.size() + 1 > cap) return fail(DISO_E_INVALID, "profile buffer too small (%zu needed)", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return DISO_OK;
+}
 
 size_t diso_b200_state_bytes(int alg, int X, int Y, int Z)
 {
@@ -293,13 +359,10 @@ int diso_b200_quad_split(const void *verts, int dtype, const int64_t *quads, int
     unsigned *tile_cnt = reinterpret_cast<unsigned *>(b + 256);
     unsigned char *flags = reinterpret_cast<unsigned char *>(b + 256 + align_up((size_t)tiles * 4 + 4, 256));
     const long long *qd = reinterpret_cast<const long long *>(quads);
-    if (dtype == DISO_F32) quad_diag_kernel<float><<<tiles, QS_TILE, 0, st>>>(static_cast<const float *>(verts), qd, n_quads, flags, tile_cnt);
-    else quad_diag_kernel<double><<<tiles, QS_TILE, 0, st>>>(static_cast<const double *>(verts), qd, n_quads, flags, tile_cnt);
-    CU_LAUNCH_CHECK("quad_diag");
-    tile_scan_kernel<<<1, 1024, 0, st>>>(tile_cnt, tiles, total);
-    CU_LAUNCH_CHECK("tile_scan");
-    quad_emit_kernel<<<tiles, QS_TILE, 0, st>>>(qd, n_quads, flags, tile_cnt, total, reinterpret_cast<long long *>(faces));
-    CU_LAUNCH_CHECK("quad_emit");
+    if (dtype == DISO_F32) LAUNCH("quad_diag", st, quad_diag_kernel<float><<<tiles, QS_TILE, 0, st>>>(static_cast<const float *>(verts), qd, n_quads, flags, tile_cnt));
+    else LAUNCH("quad_diag", st, quad_diag_kernel<double><<<tiles, QS_TILE, 0, st>>>(static_cast<const double *>(verts), qd, n_quads, flags, tile_cnt));
+    LAUNCH("quad_tile_scan", st, tile_scan_kernel<<<1, 1024, 0, st>>>(tile_cnt, tiles, total));
+    LAUNCH("quad_emit", st, quad_emit_kernel<<<tiles, QS_TILE, 0, st>>>(qd, n_quads, flags, tile_cnt, total, reinterpret_cast<long long *>(faces)));
     return DISO_OK;
 }
 
@@ -313,10 +376,9 @@ int diso_b200_debug_cell_codes(int alg, int X, int Y, int Z, const void *state, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long n = (long long)g.PX * g.PY * g.PZ;
     if (alg == DISO_ALG_MC)
-        debug_codes_kernel<DISO_ALG_MC><<<cdiv(n, 256), 256, 0, st>>>(g, p.S, nullptr, codes);
+        LAUNCH("debug_codes", st, debug_codes_kernel<DISO_ALG_MC><<<cdiv(n, 256), 256, 0, st>>>(g, p.S, nullptr, codes));
     else
-        debug_codes_kernel<DISO_ALG_DMC><<<cdiv(n, 256), 256, 0, st>>>(g, p.S, reinterpret_cast<const uint4 *>(p.aux), codes);
-    CU_LAUNCH_CHECK("debug_codes");
+        LAUNCH("debug_codes", st, debug_codes_kernel<DISO_ALG_DMC><<<cdiv(n, 256), 256, 0, st>>>(g, p.S, reinterpret_cast<const uint4 *>(p.aux), codes));
     return DISO_OK;
 }
 

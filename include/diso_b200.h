@@ -113,6 +113,17 @@ size_t diso_b200_quad_split_scratch_bytes(int64_t n_quads);
 int diso_b200_quad_split(const void *verts, int dtype, const int64_t *quads, int64_t n_quads,
                          void *scratch, int64_t *faces, void *stream);
 
+/* Tracing (the reference has none).  diso_b200_launch_count: number of
+ * kernels this library has launched in the process.  diso_b200_profile_enable(1) makes every
+ * subsequent launch (process-wide: autograd issues backward from its own thread) record a
+ * CUDA-event pair on its stream;
+ * diso_b200_profile_dump waits for them and writes one "kernel_name milliseconds" line per
+ * launch into buf (NUL-terminated), then clears the list.  Used by bench.py for the live
+ * per-kernel roofline figure; off by default (no events, no overhead). */
+long long diso_b200_launch_count(void);
+int diso_b200_profile_enable(int on);
+int diso_b200_profile_dump(char *buf, size_t cap);
+
 /* Test / diagnostics hook: expands the rank structure into the reference's intermediate
  * "case index per cell" so parity tests can compare the active-cell set and the 8-bit case
  * index bit-exactly (reference: used_cell_index / used_cell_code, cumc.cu:299-311,540-562).

@@ -173,7 +173,8 @@ def split_quads(verts, quads):
     as verts): for both diagonals, max cosine over the 2x3 triangle angles with
     x / max(||x||, 1e-12); config 1 ([0,1,3],[1,2,3]) iff angles1 < angles2; output groups all
     config-1 quads first, then config-2 quads, each in quad order.
-    Returns (faces int64 [2Q,3], n_config1)."""
+    Returns (faces int64 [2Q,3], n_config1, margin [Q] = |angles1 - angles2|); quads with a
+    margin near 0 are ties whose diagonal is decided by the last bit of the arithmetic."""
     dt = verts.dtype
     quads = quads.astype(np.int64)
 
@@ -193,4 +194,4 @@ def split_quads(verts, quads):
     sel = a1 < a2
     f1 = quads[sel][:, [0, 1, 3, 1, 2, 3]].reshape(-1, 3)
     f2 = quads[~sel][:, [0, 1, 2, 0, 2, 3]].reshape(-1, 3)
-    return np.concatenate([f1, f2], 0), int(sel.sum())
+    return np.concatenate([f1, f2], 0), int(sel.sum()), np.abs(a1.astype(np.float64) - a2.astype(np.float64))

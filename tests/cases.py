@@ -23,19 +23,20 @@ CASES = {
     # name: (sdf factory, use deform, iso)
     "sphere32": (lambda: syn.sphere_sdf(32, margin=1 / 32), False, 0.0),
     "sphere64": (lambda: syn.sphere_sdf(64), False, 0.0),                     # BASELINE C1
-    "roundcube48_def": (lambda: syn.round_cube_sdf(48), True, 0.0),             # BASELINE C2 in miniature
-    "rand_flexi_40": (lambda: syn.random_sdf(40, "flexi", 0), True, 0.0),       # C3/C4 in miniature
-    "rand_dense_33": (lambda: syn.random_sdf(33, "dense", 0), True, 0.0),       # worst case, odd size
+    "roundcube32_def": (lambda: syn.round_cube_sdf(32), True, 0.0),             # BASELINE C2 in miniature
+    "rand_flexi_24": (lambda: syn.random_sdf(24, "flexi", 0), True, 0.0),       # C3/C4 in miniature
+    "rand_dense_19": (lambda: syn.random_sdf(19, "dense", 0), True, 0.0),       # worst case, odd size
     "rand_sparse_36": (lambda: syn.random_sdf(36, "sparse", 0), False, 0.0),
+    "rand_dense_40x33x70": (lambda: syn.random_sdf((40, 33, 70), "dense", 12), True, 0.0),  # larger; no golden, oracle only
     "ragged_5x9x70": (lambda: syn.random_sdf((5, 9, 70), "dense", 3), True, 0.0),   # 3 chunks per row, Z%4!=0
     "ragged_31x2x30": (lambda: syn.random_sdf((31, 2, 30), "flexi", 4), True, 0.0),  # PZ == 32 exactly
     "ragged_3x4x62": (lambda: syn.random_sdf((3, 4, 62), "dense", 5), False, 0.0),   # PZ == 64 exactly
     "tiny_1x1x1": (lambda: torch.full((1, 1, 1), -0.3), True, 0.0),
     "tiny_2x2x2": (lambda: syn.random_sdf(2, "dense", 6), True, 0.0),
     "thin_1x7x33": (lambda: syn.random_sdf((1, 7, 33), "dense", 7), True, 0.0),
-    "iso_0p37": (lambda: syn.random_sdf(24, "dense", 8) + 0.5, True, 0.37),
+    "iso_0p37": (lambda: syn.random_sdf(14, "dense", 8) + 0.5, True, 0.37),
     "iso_neg": (lambda: syn.sphere_sdf(24, margin=1 / 24), False, -0.05),
-    "ties_int": (lambda: _ints((12, 13, 37), 9), True, 0.0),                       # values == iso
+    "ties_int": (lambda: _ints((6, 7, 37), 9), True, 0.0),                       # values == iso
     "plane_x": (lambda: _plane((9, 8, 40), 0, 3.5), False, 0.0),
     "plane_z_tie": (lambda: _plane((6, 7, 34), 2, 16.0), False, 0.0),              # a whole layer == iso
     "all_inside_but_one": (lambda: torch.ones(6, 6, 6).index_put((torch.tensor(2), torch.tensor(3), torch.tensor(4)), torch.tensor(-1.0)), True, 0.0),

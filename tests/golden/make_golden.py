@@ -27,11 +27,12 @@ sys.path.insert(0, ROOT)
 
 from tests import cases  # noqa: E402
 
-GOLDEN_CASES = ["sphere32", "sphere64", "roundcube48_def", "rand_flexi_40", "rand_dense_33", "rand_sparse_36",
+GOLDEN_CASES = ["sphere32", "sphere64", "roundcube32_def", "rand_flexi_24", "rand_dense_19", "rand_sparse_36",
                 "ragged_5x9x70", "ragged_31x2x30", "ragged_3x4x62", "tiny_1x1x1", "tiny_2x2x2", "thin_1x7x33",
                 "iso_0p37", "iso_neg", "ties_int", "plane_x", "plane_z_tie", "all_inside_but_one",
                 "boundary_negative"]
-F64_CASES = {"sphere32", "rand_flexi_40", "ragged_5x9x70", "ties_int", "iso_0p37"}
+F64_CASES = {"sphere32", "rand_flexi_24", "ragged_5x9x70", "ties_int", "iso_0p37"}
+UNNORMALISED_CASES = {"sphere32", "ragged_5x9x70", "thin_1x7x33"}
 
 
 def load_reference():
@@ -87,19 +88,21 @@ def main():
             sd = sdf.to(dev)
             df = deform.to(dev) if deform is not None else None
             mc, dmc = ref.DiffMC(dtype=dtype), ref.DiffDMC(dtype=dtype)
-            for key, mod, kw in (("mc", mc, {}), ("dmcq", dmc, dict(return_quads=True)), ("dmct", dmc, dict(return_quads=False))):
-                for norm in (True, False):
-                    if norm is False and key == "dmct":
-                        continue
-                    r = run_one(mod, sd, df, iso, norm, **kw)
-                    pre = "%s_%s" % (key, "n" if norm else "u")
-                    arrays[pre + "_verts"] = r["verts"]
-                    arrays[pre + "_faces"] = r["faces"].astype(np.int32) if r["faces"].dtype == np.int64 else r["faces"]
-                    meta[pre + "_faces_dtype"] = str(r["faces"].dtype)
-                    if "gsdf" in r:
-                        arrays[pre + "_gsdf"] = r["gsdf"]
-                    if "gdef" in r:
-                        arrays[pre + "_gdef"] = r["gdef"]
+            variants = [("mc", mc, {}, True), ("dmcq", dmc, dict(return_quads=True), True)]
+            if tag == "f32":
+                variants.append(("dmct", dmc, dict(return_quads=False), True))
+            if name in UNNORMALISED_CASES:
+                variants += [("mc", mc, {}, False), ("dmcq", dmc, dict(return_quads=True), False)]
+            for key, mod, kw, norm in variants:
+                r = run_one(mod, sd, df, iso, norm, **kw)
+                pre = "%s_%s" % (key, "n" if norm else "u")
+                arrays[pre + "_verts"] = r["verts"]
+                arrays[pre + "_faces"] = r["faces"].astype(np.int32) if r["faces"].dtype == np.int64 else r["faces"]
+                meta[pre + "_faces_dtype"] = str(r["faces"].dtype)
+                if "gsdf" in r:
+                    arrays[pre + "_gsdf"] = r["gsdf"]
+                if "gdef" in r:
+                    arrays[pre + "_gdef"] = r["gdef"]
             arrays["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
             path = os.path.join(args.out, "%s_%s.npz" % (name, tag))
             np.savez_compressed(path, **arrays)

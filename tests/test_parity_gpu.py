@@ -43,12 +43,16 @@ def close(a, b, dtype, what):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     assert a.shape == b.shape, what
+    # non-finite values (a grid dimension of 1 makes `dims - 1` zero, as in the reference) must match exactly
+    fin = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), fin) and np.array_equal(a[~fin], b[~fin], equal_nan=True), what + ": non-finite pattern"
+    a, b = a[fin], b[fin]
     scale = max(1.0, float(np.abs(b).max()) if b.size else 1.0)
     err = float(np.abs(a - b).max()) if a.size else 0.0
     assert err <= TOL[dtype] * scale * 4, "%s: max err %.3e (scale %.3e)" % (what, err, scale)
 
 
-F64 = {"sphere32", "rand_flexi_40", "ragged_5x9x70", "ties_int", "iso_0p37", "tiny_2x2x2"}
+F64 = {"sphere32", "rand_flexi_24", "ragged_5x9x70", "ties_int", "iso_0p37", "tiny_2x2x2"}
 PARAMS = [(n, torch.float32) for n in cases.CASES] + [(n, torch.float64) for n in sorted(F64)]
 
 
@@ -67,7 +71,7 @@ def test_forward_backward_vs_oracle(oracle, name, dtype, alg):
             continue
         assert got["faces_dtype"] == torch.int64
         assert np.array_equal(got["faces"], ef), "face connectivity differs"
-        assert np.array_equal(got["verts"], ev), "vertices not bit-identical: max err %.3e" % np.abs(got["verts"] - ev).max()
+        assert np.array_equal(got["verts"], ev, equal_nan=True), "vertices not bit-identical: max err %.3e" % np.nanmax(np.abs(got["verts"] - ev))
         w = weights(ev.shape[0], dtype).numpy()
         egs, egd = oracle.backward(alg, sn, dn, iso, normalize, w, "reference")
         close(got["gsdf"], egs, dtype, "adj_sdf")
@@ -75,7 +79,7 @@ def test_forward_backward_vs_oracle(oracle, name, dtype, alg):
             close(got["gdef"], egd, dtype, "adj_deform")
 
 
-@pytest.mark.parametrize("name", ["rand_dense_33", "ragged_5x9x70", "ties_int", "boundary_negative"])
+@pytest.mark.parametrize("name", ["rand_dense_19", "ragged_5x9x70", "ties_int", "boundary_negative"])
 def test_dmc_exact_grad_mode_vs_oracle(oracle, name):
     for dtype in (torch.float32, torch.float64):
         sdf, deform, iso = cases.make(name, dtype)
@@ -87,7 +91,7 @@ def test_dmc_exact_grad_mode_vs_oracle(oracle, name):
 
 
 @pytest.mark.parametrize("alg", ["mc", "dmc"])
-@pytest.mark.parametrize("name", ["sphere64", "rand_dense_33", "ragged_5x9x70", "ties_int", "thin_1x7x33"])
+@pytest.mark.parametrize("name", ["sphere64", "rand_dense_19", "ragged_5x9x70", "ties_int", "thin_1x7x33"])
 def test_case_index_and_active_cells_bit_exact(oracle, alg, name):
     import diso_b200
     sdf, _, iso = cases.make(name)
@@ -119,7 +123,7 @@ def test_quad_split_vs_torch_reference_code():
     bar is: identical output for all quads whose two scores differ by more than 1e-6."""
     import torch.nn.functional as F
     import diso_b200
-    for name in ("rand_dense_33", "roundcube48_def", "sphere32"):
+    for name in ("rand_dense_19", "roundcube32_def", "sphere32"):
         sdf, deform, iso = cases.make(name)
         d = deform.to(DEV) if deform is not None else None
         verts, quads = diso_b200.DiffDMC()(sdf.to(DEV), d, iso, return_quads=True)
@@ -153,18 +157,19 @@ def test_quad_split_vs_torch_reference_code():
 
 def test_dmc_triangles_default_path(oracle):
     import diso_b200
-    sdf, deform, iso = cases.make("roundcube48_def")
+    sdf, deform, iso = cases.make("roundcube32_def")
     v, f = diso_b200.DiffDMC()(sdf.to(DEV), deform.to(DEV), iso)  # return_quads=False
     v2, q = diso_b200.DiffDMC()(sdf.to(DEV), deform.to(DEV), iso, return_quads=True)
     assert f.shape == (2 * q.shape[0], 3) and f.dtype == torch.int64 and torch.equal(v, v2)
-    ef, _ = oracle.split_quads(v.cpu().numpy(), q.cpu().numpy())
-    mism = (f.cpu().numpy() != ef).any(1).sum()
-    assert mism <= 0.002 * len(ef) + 4, "quad split differs from the numpy restatement on %d faces" % mism
+    ef, _, margin = oracle.split_quads(v.cpu().numpy(), q.cpu().numpy())
+    rows = lambda t: set(map(tuple, t.tolist()))
+    diff = rows(f.cpu().numpy()) ^ rows(ef)
+    assert len(diff) <= 4 * int((margin <= 1e-5).sum()), "quad split differs from the numpy restatement beyond near-ties"
 
 
 def test_noncontiguous_inputs_and_expanded_grad():
     import diso_b200
-    sdf, deform, iso = cases.make("rand_flexi_40")
+    sdf, deform, iso = cases.make("rand_flexi_24")
     s = sdf.to(DEV)
     st = s.permute(2, 1, 0).contiguous().permute(2, 1, 0)  # same values, non-contiguous
     assert not st.is_contiguous()
@@ -183,7 +188,7 @@ def test_two_extractions_interleaved_are_independent():
     import diso_b200
     m = diso_b200.DiffMC()
     a = cases.make("sphere32")[0].to(DEV).requires_grad_(True)
-    b = cases.make("rand_dense_33")[0].to(DEV).requires_grad_(True)
+    b = cases.make("rand_dense_19")[0].to(DEV).requires_grad_(True)
     va, _ = m(a)
     vb, _ = m(b)
     (va * weights(va.shape[0], torch.float32, DEV)).sum().backward()

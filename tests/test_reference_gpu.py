@@ -50,7 +50,7 @@ def _inputs(name, dtype):
     return cases.make(name, dtype)
 
 
-NAMES = list(BIG) + ["rand_dense_33", "ragged_5x9x70", "ties_int", "iso_0p37", "thin_1x7x33", "boundary_negative", "tiny_2x2x2"]
+NAMES = list(BIG) + ["rand_dense_19", "ragged_5x9x70", "ties_int", "iso_0p37", "thin_1x7x33", "boundary_negative", "tiny_2x2x2"]
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
@@ -104,7 +104,20 @@ def test_dmc_triangle_split_matches_reference(ref):
         d = deform.to(DEV) if deform is not None else None
         va, fa = diso_b200.DiffDMC()(sdf.to(DEV), d, iso)
         vb, fb = ref.DiffDMC()(sdf.to(DEV), d, iso)
-        assert fa.shape == fb.shape and fa.dtype == fb.dtype
-        mism = int((fa != fb).any(1).sum())
-        # the diagonal choice is fp-sensitive on (near-)symmetric quads; require >= 99.9 % identical rows
-        assert mism <= 1e-3 * fb.shape[0] + 8, "%s: %d of %d faces differ" % (name, mism, fb.shape[0])
+        assert fa.shape == fb.shape and fa.dtype == fb.dtype and torch.equal(va, vb)
+        # The diagonal choice is fp-sensitive on (near-)symmetric quads and one flipped quad shifts the
+        # grouped output, so compare per quad: recover each implementation's choice from its face list.
+        _, q = diso_b200.DiffDMC()(sdf.to(DEV), d, iso, return_quads=True)
+
+        def choice(faces):
+            # config-1 quads come first; a quad is config 1 iff [q0,q1,q3] is among the faces
+            key = lambda t: t[:, 0] * (va.shape[0] ** 2) + t[:, 1] * va.shape[0] + t[:, 2]
+            have = torch.sort(key(faces))[0]
+            want = key(q[:, [0, 1, 3]])
+            pos = torch.searchsorted(have, want).clamp(max=have.numel() - 1)
+            return have[pos] == want
+        ca, cb = choice(fa), choice(fb)
+        flipped = int((ca != cb).sum())
+        assert flipped <= 2e-3 * q.shape[0] + 4, "%s: %d of %d quads pick the other diagonal" % (name, flipped, q.shape[0])
+        if flipped == 0:
+            assert torch.equal(fa, fb)
