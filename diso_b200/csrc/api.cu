@@ -9,8 +9,11 @@
 #include <vector>
 
 #include "classify.cuh"
+#include "compact.cuh"
 #include "dmc.cuh"
+#include "dmc_compact.cuh"
 #include "mc.cuh"
+#include "mc_backward_tile.cuh"
 #include "quad_split.cuh"
 
 using namespace diso;
@@ -58,6 +61,7 @@ struct StatePtrs {
     unsigned *S;
     uint4 *E;
     void *aux;
+    unsigned short *C;
 };
 
 StatePtrs state_ptrs(void *state, const StateLayout &L)
@@ -70,6 +74,7 @@ StatePtrs state_ptrs(void *state, const StateLayout &L)
     p.S = reinterpret_cast<unsigned *>(b + L.off_sign);
     p.E = reinterpret_cast<uint4 *>(b + L.off_erec);
     p.aux = b + L.off_aux;
+    p.C = reinterpret_cast<unsigned short *>(b + L.off_cell);
     return p;
 }
 
@@ -80,6 +85,16 @@ template <typename T> Epilogue<T> make_epilogue(const Geo &g, int normalize)
     e.dy = T(g.Y) - T(1);
     e.dz = T(g.Z) - T(1);
     e.normalize = normalize != 0;
+    return e;
+}
+
+template <typename T> EpilogueC<T> make_epilogue_c(const Geo &g, int normalize, bool shift = true)
+{
+    EpilogueC<T> e;
+    e.dx = T(g.X) - T(1); e.dy = T(g.Y) - T(1); e.dz = T(g.Z) - T(1);
+    e.rx = T(1) / e.dx; e.ry = T(1) / e.dy; e.rz = T(1) / e.dz;
+    const bool zero_div = g.X == 1 || g.Y == 1 || g.Z == 1;
+    e.normalize = !shift ? 0 : (normalize ? (zero_div ? 3 : 2) : 1);
     return e;
 }
 
@@ -153,8 +168,8 @@ int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const 
     const int groups = cdiv(g.NCH, 32);
     const int grid = cdiv(groups, EMIT_WARPS);
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
-    const Epilogue<T> epi = make_epilogue<T>(g, normalize);
-    LAUNCH("mc_emit_verts", st, mc_emit_verts_kernel<T><<<grid, EMIT_WARPS * 32, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, verts));
+    const EpilogueC<T> epi = make_epilogue_c<T>(g, normalize);
+    LAUNCH("mc_emit_verts", st, edge_verts_kernel<T><<<cdiv(g.NCH, CT_CHUNKS), CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, verts));
     LAUNCH("mc_emit_tris", st, mc_emit_tris_kernel<<<grid, EMIT_WARPS * 32, 0, st>>>(g, p.S, p.E, reinterpret_cast<const unsigned *>(p.aux), tris));
     return DISO_OK;
 }
@@ -167,9 +182,27 @@ int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const
     const int grid = cdiv(groups, EMIT_WARPS);
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
-    const Epilogue<T> epi = make_epilogue<T>(g, normalize), epi0 = make_epilogue<T>(g, 0);
-    LAUNCH("dmc_emit_verts", st, dmc_emit_verts_kernel<T><<<grid, EMIT_WARPS * 32, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.S, P, verts));
-    LAUNCH("dmc_emit_quads", st, (dmc_edges_kernel<T, 0><<<grid, EMIT_WARPS * 32, 0, st>>>(g, p.S, p.E, P, epi0, nullptr, quads, nullptr)));
+    const Epilogue<T> epi = make_epilogue<T>(g, normalize);
+    LAUNCH("dmc_emit_verts", st, dmc_emit_verts_kernel<T><<<grid, EMIT_WARPS * 32, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.S, P, p.C, verts));
+    LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0><<<cdiv(g.NCH, CT_CHUNKS), CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, T(1), T(1), T(1), nullptr, quads, nullptr)));
+    return DISO_OK;
+}
+
+template <typename T, int TX, int TY, bool HAS_DEF, bool VEC>
+int launch_bwd_tile(const T *sdf, const T *deform, const Geo &g, T isoT, T padv, const BwdEpi<T> &epi, const uint4 *E,
+                    const T *gsrc, T *adj_sdf, T *adj_deform, cudaStream_t st)
+{
+    auto kern = mc_backward_tile_kernel<T, TX, TY, HAS_DEF, VEC>;
+    constexpr size_t smem = bwd_tile_smem<T, TX, TY, HAS_DEF>();
+    static bool configured = false;  // per instantiation; the attribute is per device function
+    if (!configured) {
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int ntx = cdiv(g.X, TX), nty = cdiv(g.Y, TY);
+    const long long grid = (long long)ntx * nty * g.NC;
+    LAUNCH("mc_backward", st, kern<<<(unsigned)grid, BT_WARPS * 32, smem, st>>>(sdf, deform, g, isoT, padv, epi, E, gsrc, adj_sdf,
+                                                                              adj_deform, ntx, nty));
     return DISO_OK;
 }
 
@@ -178,10 +211,20 @@ int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, co
                      int normalize, T *adj_sdf, T *adj_deform, cudaStream_t st)
 {
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
-    const Epilogue<T> epi = make_epilogue<T>(g, normalize);
-    LAUNCH("mc_backward", st, mc_backward_kernel<T><<<cdiv(g.NCH, EMIT_WARPS), EMIT_WARPS * 32, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E,
-                                                                                                      adj_verts, adj_sdf, adj_deform));
-    return DISO_OK;
+    BwdEpi<T> epi;
+    epi.ix = normalize ? T(1) / (T(g.X) - T(1)) : T(1);
+    epi.iy = normalize ? T(1) / (T(g.Y) - T(1)) : T(1);
+    epi.iz = normalize ? T(1) / (T(g.Z) - T(1)) : T(1);
+    constexpr int VN = 16 / sizeof(T);
+    const bool vec = (g.Z % VN == 0) && ((reinterpret_cast<uintptr_t>(sdf) & 15) == 0) &&
+                     (!deform || (reinterpret_cast<uintptr_t>(deform) & 15) == 0);
+    constexpr int TX = sizeof(T) == 4 ? 8 : 4, TY = 8;
+    if (deform) {
+        if (vec) return launch_bwd_tile<T, TX, TY, true, true>(sdf, deform, g, isoT, padv, epi, p.E, adj_verts, adj_sdf, adj_deform, st);
+        return launch_bwd_tile<T, TX, TY, true, false>(sdf, deform, g, isoT, padv, epi, p.E, adj_verts, adj_sdf, adj_deform, st);
+    }
+    if (vec) return launch_bwd_tile<T, TX, TY, false, true>(sdf, deform, g, isoT, padv, epi, p.E, adj_verts, adj_sdf, adj_deform, st);
+    return launch_bwd_tile<T, TX, TY, false, false>(sdf, deform, g, isoT, padv, epi, p.E, adj_verts, adj_sdf, adj_deform, st);
 }
 
 template <typename T>
@@ -191,11 +234,13 @@ int dmc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, c
     const int groups = cdiv(g.NCH, 32);
     const int grid = cdiv(groups, EMIT_WARPS);
     const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
-    const Epilogue<T> epi = make_epilogue<T>(g, normalize);
+    const T ix = normalize ? T(1) / (T(g.X) - T(1)) : T(1), iy = normalize ? T(1) / (T(g.Y) - T(1)) : T(1),
+            iz = normalize ? T(1) / (T(g.Z) - T(1)) : T(1);
+    const int grid2 = cdiv(g.NCH, CT_CHUNKS);
     if (grad_mode == DISO_GRAD_EXACT)
-        LAUNCH("dmc_edge_adjoint", st, (dmc_edges_kernel<T, 1><<<grid, EMIT_WARPS * 32, 0, st>>>(g, p.S, p.E, P, epi, adj_verts, nullptr, scratch)));
+        LAUNCH("dmc_edge_adjoint", st, (dmc_edges2_kernel<T, 1><<<grid2, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, ix, iy, iz, adj_verts, nullptr, scratch)));
     else
-        LAUNCH("dmc_edge_adjoint", st, (dmc_edges_kernel<T, 2><<<grid, EMIT_WARPS * 32, 0, st>>>(g, p.S, p.E, P, epi, adj_verts, nullptr, scratch)));
+        LAUNCH("dmc_edge_adjoint", st, (dmc_edges2_kernel<T, 2><<<grid2, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, ix, iy, iz, adj_verts, nullptr, scratch)));
     return mc_backward_impl<T>(sdf, deform, g, iso, p, scratch, 0, adj_sdf, adj_deform, st);
 }
 

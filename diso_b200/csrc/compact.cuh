@@ -1,0 +1,149 @@
+// compact.cuh -- CTA-level work compaction shared by the emit kernels.
+//
+// Only ~18 % of the (grid point, axis) slots of a random-init SDF carry a crossing edge (and
+// far fewer on smooth surfaces), so a lane-per-point kernel idles most of its lanes: the ncu
+// baseline (profiles/r1_base_*.txt) shows every such kernel issue-bound with ~15 of 32 threads
+// active.  Instead each CTA owns CT_CHUNKS consecutive chunks and works in two phases:
+//   phase A  lane == grid point: decode the chunk's edge record and drop a 16-bit descriptor
+//            {chunk-in-tile, lane, axis} for every crossing edge into a shared list.  Because the
+//            records carry GLOBAL exclusive prefix sums, the list slot of an edge is simply
+//            rank - rank_of_first_edge_of_tile: no scan, and list order == output order.
+//   phase B  thread == list entry: fully populated warps evaluate one edge each and write the
+//            result at consecutive output ranks (dense, coalesced stores).
+#pragma once
+#include "classify.cuh"
+#include "edge_math.cuh"
+
+namespace diso {
+
+constexpr int CT_CHUNKS = 64;    // chunks per CTA tile
+constexpr int CT_THREADS = 256;  // threads per CTA
+constexpr int CT_WARPS = CT_THREADS / 32;
+constexpr int CT_MAX_EDGES = CT_CHUNKS * 96;
+
+struct TilePos { short xp, yp, c, pad; };
+
+__device__ __forceinline__ unsigned short edge_desc(int chunk_local, int lane, int axis)
+{
+    return (unsigned short)((chunk_local << 7) | (lane << 2) | axis);
+}
+
+// Phase A for edge lists.  Fills s_list[rank - tile_base] and s_pos[chunk_local]; returns the
+// number of edges of the tile (uniform).  Must be called by all CT_THREADS threads.
+// If S != nullptr, bit 13 of each descriptor tells whether the edge's start point is inside
+// (value >= iso), i.e. whether the crossing is "exiting" in the DMC sense (cudualmc.cu:782-788).
+__device__ __forceinline__ unsigned build_edge_list(const Geo &g, const uint4 *__restrict__ E, int k0,
+                                                    unsigned short *s_list, TilePos *s_pos, unsigned &tile_base,
+                                                    const unsigned *__restrict__ S = nullptr)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int kend = min(k0 + CT_CHUNKS, g.NCH);
+    tile_base = E[k0].x;
+    const unsigned n = E[kend].x - tile_base;  // E[NCH] holds the grand total
+    if (n == 0) return 0;
+    // each warp: chunks k0 + wid*8 .. +7 ; lanes 0..7 fetch the records, then broadcast
+    constexpr int PER_WARP = CT_CHUNKS / CT_WARPS;
+    uint4 mine = make_uint4(0, 0, 0, 0);
+    const int kmine = k0 + wid * PER_WARP + lane;
+    if (lane < PER_WARP && kmine < kend) mine = E[kmine];
+    unsigned active = __ballot_sync(FULL, (mine.y | mine.z | mine.w) != 0u);
+    if (lane < PER_WARP && kmine < kend) {
+        const int r = kmine / g.NC;
+        TilePos tp;
+        tp.c = (short)(kmine - r * g.NC);
+        tp.xp = (short)(r / g.PY);
+        tp.yp = (short)(r - (r / g.PY) * g.PY);
+        tp.pad = 0;
+        s_pos[wid * PER_WARP + lane] = tp;
+    }
+    const unsigned lt = lanemask_lt(lane);
+    while (active) {
+        const int i = __ffs(active) - 1;
+        active &= active - 1;
+        const unsigned base = __shfl_sync(FULL, mine.x, i), mx = __shfl_sync(FULL, mine.y, i);
+        const unsigned my = __shfl_sync(FULL, mine.z, i), mz = __shfl_sync(FULL, mine.w, i);
+        const int cl = wid * PER_WARP + i;
+        unsigned slot = base - tile_base + __popc(mx & lt) + __popc(my & lt) + __popc(mz & lt);
+        unsigned short in13 = 0;
+        if (S) in13 = (unsigned short)(bit(S[k0 + cl], lane) << 13);
+        if (bit(mx, lane)) s_list[slot++] = edge_desc(cl, lane, 0) | in13;
+        if (bit(my, lane)) s_list[slot++] = edge_desc(cl, lane, 1) | in13;
+        if (bit(mz, lane)) s_list[slot] = edge_desc(cl, lane, 2) | in13;
+    }
+    return n;
+}
+
+// IEEE-correct x / d for a divisor d whose correctly rounded reciprocal r = RN(1/d) is known
+// (Markstein's sequence: q = RN(x r); rem = x - q d exactly by FMA; result = RN(q + rem r)).
+// Correctly rounded for normal operands unless d's significand is all ones; our divisors are
+// small integers (dims - 1).  Verified bit-for-bit against the division in tests.
+template <typename T> __device__ __forceinline__ T div_by_const(T x, T d, T r)
+{
+    const T q = x * r;
+    const T rem = fma_rn(-q, d, x);
+    return fma_rn(rem, r, q);
+}
+
+template <typename T> struct EpilogueC {
+    T dx, dy, dz;  // (T)dim - 1
+    T rx, ry, rz;  // RN(1 / (dim - 1))
+    int normalize; // 0: raw padded frame (no shift), 1: (p-1), 2: (p-1)/(dim-1) via div_by_const,
+                   // 3: (p-1)/(dim-1) by plain division (some dim == 1, i.e. a zero divisor)
+    __device__ __forceinline__ Vec3<T> apply(Vec3<T> p) const
+    {
+        if (normalize == 0) return p;
+        p.x = p.x - T(1); p.y = p.y - T(1); p.z = p.z - T(1);
+        if (normalize == 2) {
+            p.x = div_by_const(p.x, dx, rx); p.y = div_by_const(p.y, dy, ry); p.z = div_by_const(p.z, dz, rz);
+        } else if (normalize == 3) {
+            p.x = p.x / dx; p.y = p.y / dy; p.z = p.z / dz;
+        }
+        return p;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// K3 (v2): edge vertices, edge-parallel.  Replaces create_cell_mc_verts_kernel
+// (cumc.cu:370-410) + the "-1"/normalise epilogue (diso/__init__.py:56-60).  With
+// epi.normalize == 0 it produces the raw padded-frame crossings that the DMC dual-vertex
+// kernel averages (computeMcVert of cudualmc.cu:683-708, each edge evaluated once, not 4x).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(CT_THREADS) edge_verts_kernel(const T *__restrict__ sdf, const T *__restrict__ deform,
+                                                              Geo g, T iso, T padv, EpilogueC<T> epi,
+                                                              const uint4 *__restrict__ E, T *__restrict__ verts)
+{
+    __shared__ unsigned short s_list[CT_MAX_EDGES];
+    __shared__ TilePos s_pos[CT_CHUNKS];
+    const int k0 = blockIdx.x * CT_CHUNKS;
+    unsigned tile_base;
+    const unsigned n = build_edge_list(g, E, k0, s_list, s_pos, tile_base);
+    if (n == 0) return;
+    __syncthreads();
+    const bool has_def = deform != nullptr;
+    for (unsigned i = threadIdx.x; i < n; i += CT_THREADS) {
+        const unsigned d = s_list[i];
+        const int axis = d & 3, j = (d >> 2) & 31;
+        const TilePos tp = s_pos[(d >> 7) & 63];
+        const int xp = tp.xp, yp = tp.yp, zp = 32 * tp.c + j;
+        const int xq = xp + (axis == 0), yq = yp + (axis == 1), zq = zp + (axis == 2);
+        const T d0 = fetch_padded(sdf, g, xp, yp, zp, padv);
+        const T d1 = fetch_padded(sdf, g, xq, yq, zq, padv);
+        const T t = edge_t(d0, d1, iso);
+        Vec3<T> p0{T(xp), T(yp), T(zp)}, p1{T(xq), T(yq), T(zq)};
+        if (has_def) {
+            const Vec3<T> f0 = fetch_deform(deform, g, xp, yp, zp), f1 = fetch_deform(deform, g, xq, yq, zq);
+            p0.x = p0.x + f0.x; p0.y = p0.y + f0.y; p0.z = p0.z + f0.z;
+            p1.x = p1.x + f1.x; p1.y = p1.y + f1.y; p1.z = p1.z + f1.z;
+        }
+        Vec3<T> p;
+        p.x = fma_rn(p1.x - p0.x, t, p0.x);
+        p.y = fma_rn(p1.y - p0.y, t, p0.y);
+        p.z = fma_rn(p1.z - p0.z, t, p0.z);
+        p = epi.apply(p);
+        T *dst = verts + (size_t)(tile_base + i) * 3;
+        st_stream(dst, p.x); st_stream(dst + 1, p.y); st_stream(dst + 2, p.z);
+    }
+}
+
+}  // namespace diso

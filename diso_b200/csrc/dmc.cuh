@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) dmc_emit_verts_kernel(const T
                                                                        T padv, Epilogue<T> epi,
                                                                        const unsigned *__restrict__ S,
                                                                        const uint4 *__restrict__ P,
+                                                                       unsigned short *__restrict__ C,
                                                                        T *__restrict__ verts)
 {
     __shared__ unsigned s_case[256];
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) dmc_emit_verts_kernel(const T
         const ChunkPos cp = chunk_pos(g, k);
         const int xp = cp.xp, yp = cp.yp, zp = 32 * cp.c + lane;
         const CellInfo ci = dmc_cell_info(S, P, g, s_case, k, lane);
+        C[(size_t)k * 32 + lane] = ci.ce ? (unsigned short)(ci.code | ((ci.first - vbase) << 8)) : (unsigned short)0;
         if (ci.ce) {
             const unsigned np = (ci.ce >> 24) & 7u;
             const unsigned plen = s_plen[ci.code];
