@@ -13,7 +13,7 @@
 #include "dmc.cuh"
 #include "dmc_compact.cuh"
 #include "mc.cuh"
-#include "mc_backward_tile.cuh"
+#include "mc_backward_compact.cuh"
 #include "quad_split.cuh"
 
 using namespace diso;
@@ -182,27 +182,27 @@ int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const
     const int grid = cdiv(groups, EMIT_WARPS);
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
-    const Epilogue<T> epi = make_epilogue<T>(g, normalize);
-    LAUNCH("dmc_emit_verts", st, dmc_emit_verts_kernel<T><<<grid, EMIT_WARPS * 32, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.S, P, p.C, verts));
+    const EpilogueC<T> epic = make_epilogue_c<T>(g, normalize);
+    LAUNCH("dmc_emit_verts", st, dmc_dual_verts_kernel<T><<<cdiv(g.NCH, CT_CHUNKS), CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epic, p.S, P, p.C, verts));
     LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0><<<cdiv(g.NCH, CT_CHUNKS), CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, T(1), T(1), T(1), nullptr, quads, nullptr)));
     return DISO_OK;
 }
 
-template <typename T, int TX, int TY, bool HAS_DEF, bool VEC>
-int launch_bwd_tile(const T *sdf, const T *deform, const Geo &g, T isoT, T padv, const BwdEpi<T> &epi, const uint4 *E,
-                    const T *gsrc, T *adj_sdf, T *adj_deform, cudaStream_t st)
+template <typename T, bool HAS_DEF>
+int launch_bwd_compact(const T *sdf, const T *deform, const Geo &g, T isoT, T padv, T ix, T iy, T iz, const uint4 *E,
+                       const T *gsrc, T *adj_sdf, T *adj_deform, cudaStream_t st)
 {
-    auto kern = mc_backward_tile_kernel<T, TX, TY, HAS_DEF, VEC>;
-    constexpr size_t smem = bwd_tile_smem<T, TX, TY, HAS_DEF>();
-    static bool configured = false;  // per instantiation; the attribute is per device function
+    auto kern = mc_backward_compact_kernel<T, HAS_DEF>;
+    constexpr size_t smem = bwd_compact_smem<T, HAS_DEF>();
+    static bool configured = false;  // per instantiation
     if (!configured) {
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    const int ntx = cdiv(g.X, TX), nty = cdiv(g.Y, TY);
+    const int ntx = cdiv(g.X, BC_X), nty = cdiv(g.Y, BC_Y);
     const long long grid = (long long)ntx * nty * g.NC;
-    LAUNCH("mc_backward", st, kern<<<(unsigned)grid, BT_WARPS * 32, smem, st>>>(sdf, deform, g, isoT, padv, epi, E, gsrc, adj_sdf,
-                                                                              adj_deform, ntx, nty));
+    LAUNCH("mc_backward", st, kern<<<(unsigned)grid, BC_THREADS, smem, st>>>(sdf, deform, g, isoT, padv, ix, iy, iz, E, gsrc, adj_sdf,
+                                                                           adj_deform, ntx, nty));
     return DISO_OK;
 }
 
@@ -211,20 +211,11 @@ int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, co
                      int normalize, T *adj_sdf, T *adj_deform, cudaStream_t st)
 {
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
-    BwdEpi<T> epi;
-    epi.ix = normalize ? T(1) / (T(g.X) - T(1)) : T(1);
-    epi.iy = normalize ? T(1) / (T(g.Y) - T(1)) : T(1);
-    epi.iz = normalize ? T(1) / (T(g.Z) - T(1)) : T(1);
-    constexpr int VN = 16 / sizeof(T);
-    const bool vec = (g.Z % VN == 0) && ((reinterpret_cast<uintptr_t>(sdf) & 15) == 0) &&
-                     (!deform || (reinterpret_cast<uintptr_t>(deform) & 15) == 0);
-    constexpr int TX = sizeof(T) == 4 ? 8 : 4, TY = 8;
-    if (deform) {
-        if (vec) return launch_bwd_tile<T, TX, TY, true, true>(sdf, deform, g, isoT, padv, epi, p.E, adj_verts, adj_sdf, adj_deform, st);
-        return launch_bwd_tile<T, TX, TY, true, false>(sdf, deform, g, isoT, padv, epi, p.E, adj_verts, adj_sdf, adj_deform, st);
-    }
-    if (vec) return launch_bwd_tile<T, TX, TY, false, true>(sdf, deform, g, isoT, padv, epi, p.E, adj_verts, adj_sdf, adj_deform, st);
-    return launch_bwd_tile<T, TX, TY, false, false>(sdf, deform, g, isoT, padv, epi, p.E, adj_verts, adj_sdf, adj_deform, st);
+    // chain rule of verts / (dims - 1): multiply by the reciprocal (gradients carry a 1e-5 bar, not bit parity)
+    const T ix = normalize ? T(1) / (T(g.X) - T(1)) : T(1), iy = normalize ? T(1) / (T(g.Y) - T(1)) : T(1),
+            iz = normalize ? T(1) / (T(g.Z) - T(1)) : T(1);
+    if (deform) return launch_bwd_compact<T, true>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, adj_verts, adj_sdf, adj_deform, st);
+    return launch_bwd_compact<T, false>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, adj_verts, adj_sdf, adj_deform, st);
 }
 
 template <typename T>

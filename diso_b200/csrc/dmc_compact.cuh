@@ -80,3 +80,115 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
 }
 
 }  // namespace diso
+
+namespace diso {
+
+constexpr int CT_MAX_PATCHES = CT_CHUNKS * 128;
+
+// ------------------------------------------------------------------------------------------
+// K3d (v2): dual vertices, patch-parallel.  Replaces create_dmc_verts_kernel
+// (cudualmc.cu:907-955) + epilogue (diso/__init__.py:110-114).
+//   phase A  lane == cell: (possibly complemented) case index, patch count and first-dual-
+//            vertex id of every cell of the tile's active chunks -> per-cell array C (global,
+//            consumed by the quad / adjoint kernels) + one descriptor per patch in the shared
+//            list at slot (dual vertex id - first id of the tile).
+//   phase B  thread == dual vertex: sum the crossings of the patch's member edges in ascending
+//            edge id (== the reference's table order, asserted in tools/extract_tables.py),
+//            scale by 1/len, apply the epilogue, store at consecutive output ranks.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(CT_THREADS) dmc_dual_verts_kernel(const T *__restrict__ sdf, const T *__restrict__ deform,
+                                                                  Geo g, T iso, T padv, EpilogueC<T> epi,
+                                                                  const unsigned *__restrict__ S,
+                                                                  const uint4 *__restrict__ P,
+                                                                  unsigned short *__restrict__ C, T *__restrict__ verts)
+{
+    __shared__ unsigned short s_list[CT_MAX_PATCHES];
+    __shared__ unsigned short s_cell[CT_CHUNKS * 32];
+    __shared__ TilePos s_pos[CT_CHUNKS];
+    __shared__ unsigned s_case[256];
+    __shared__ unsigned s_plen[256];
+    __shared__ T s_inv[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int k0 = blockIdx.x * CT_CHUNKS;
+    const int kend = min(k0 + CT_CHUNKS, g.NCH);
+    const unsigned tile_base = P[k0].x;
+    const unsigned n = P[kend].x - tile_base;
+    if (n == 0) return;
+    s_case[threadIdx.x] = T_DMC_CASE[threadIdx.x];
+    s_plen[threadIdx.x] = T_DMC_PATCHLEN[threadIdx.x];
+    if (threadIdx.x < 8) s_inv[threadIdx.x] = threadIdx.x ? T(1) / T((int)threadIdx.x) : T(0);
+    __syncthreads();
+
+    // ---- phase A ---------------------------------------------------------------------------------
+    constexpr int PER_WARP = CT_CHUNKS / CT_WARPS;
+    {
+        const int kmine = k0 + wid * PER_WARP + lane;
+        bool act = false;
+        if (lane < PER_WARP && kmine < kend) {
+            act = P[kmine + 1].x != P[kmine].x;
+            const int r = kmine / g.NC;
+            TilePos tp;
+            tp.c = (short)(kmine - r * g.NC);
+            tp.xp = (short)(r / g.PY);
+            tp.yp = (short)(r - (r / g.PY) * g.PY);
+            tp.pad = 0;
+            s_pos[wid * PER_WARP + lane] = tp;
+        }
+        unsigned active = __ballot_sync(FULL, act);
+        while (active) {
+            const int i = __ffs(active) - 1;
+            active &= active - 1;
+            const int cl = wid * PER_WARP + i, k = k0 + cl;
+            const CellInfo ci = dmc_cell_info(S, P, g, s_case, k, lane);
+            const unsigned short info = ci.ce ? (unsigned short)(ci.code | ((ci.first - P[k].x) << 8)) : (unsigned short)0;
+            C[(size_t)k * 32 + lane] = info;
+            s_cell[cl * 32 + lane] = info;
+            const unsigned np = (ci.ce >> 24) & 7u;
+            const unsigned slot = ci.first - tile_base;
+#pragma unroll
+            for (unsigned q = 0; q < 4; ++q)
+                if (q < np) s_list[slot + q] = (unsigned short)((cl << 7) | (lane << 2) | q);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B ---------------------------------------------------------------------------------
+    const bool has_def = deform != nullptr;
+    for (unsigned i = threadIdx.x; i < n; i += CT_THREADS) {
+        const unsigned d = s_list[i];
+        const unsigned q = d & 3u;
+        const int j = (d >> 2) & 31, cl = (d >> 7) & 63;
+        const TilePos tp = s_pos[cl];
+        const int xp = tp.xp, yp = tp.yp, zp = 32 * tp.c + j;
+        const unsigned code = s_cell[cl * 32 + j] & 0xffu;
+        const unsigned ce = s_case[code], plen = s_plen[code];
+        Vec3<T> acc{T(0), T(0), T(0)};
+        for (unsigned m = plen >> 16; m; m &= m - 1) {  // crossing edges of the case, ascending id
+            const int e = __ffs(m) - 1;
+            if (((ce >> (2 * e)) & 3u) != q) continue;
+            const int ax = (EDGE_AX >> (2 * e)) & 3;
+            const int x0 = xp + ((EDGE_DX >> e) & 1), y0 = yp + ((EDGE_DY >> e) & 1), z0 = zp + ((EDGE_DZ >> e) & 1);
+            const int x1 = x0 + (ax == 0), y1 = y0 + (ax == 1), z1 = z0 + (ax == 2);
+            const T d0 = fetch_padded(sdf, g, x0, y0, z0, padv);
+            const T d1 = fetch_padded(sdf, g, x1, y1, z1, padv);
+            const T t = edge_t(d0, d1, iso);
+            Vec3<T> p0{T(x0), T(y0), T(z0)}, p1{T(x1), T(y1), T(z1)};
+            if (has_def) {
+                const Vec3<T> f0 = fetch_deform(deform, g, x0, y0, z0), f1 = fetch_deform(deform, g, x1, y1, z1);
+                p0.x = p0.x + f0.x; p0.y = p0.y + f0.y; p0.z = p0.z + f0.z;
+                p1.x = p1.x + f1.x; p1.y = p1.y + f1.y; p1.z = p1.z + f1.z;
+            }
+            acc.x = acc.x + fma_rn(p1.x - p0.x, t, p0.x);
+            acc.y = acc.y + fma_rn(p1.y - p0.y, t, p0.y);
+            acc.z = acc.z + fma_rn(p1.z - p0.z, t, p0.z);
+        }
+        const T inv = s_inv[(plen >> (4 * q)) & 7u];
+        Vec3<T> v{acc.x * inv, acc.y * inv, acc.z * inv};
+        v = epi.apply(v);
+        T *dst = verts + (size_t)(tile_base + i) * 3;
+        st_stream(dst, v.x); st_stream(dst + 1, v.y); st_stream(dst + 2, v.z);
+    }
+}
+
+}  // namespace diso
