@@ -117,7 +117,8 @@ def kernel_bytes(name, G, s, c_mc, c_dmc, deform):
         "mc_emit_verts": 3 * Vm * s + d3 * min(Em, G) * s,
         "mc_emit_tris": 3 * Fm * 8,
         "mc_backward": 3 * Vm * s + min(Em, G) * s + G * s + d3 * (min(Em, G) + G) * s,
-        "dmc_emit_verts": 3 * Vd * s + d3 * min(Em, G) * s,
+        "dmc_edge_crossings": d3 * min(Em, G) * s,   # internal pass: reads the deform endpoints
+        "dmc_emit_verts": 3 * Vd * s,
         "dmc_emit_quads": 4 * Qd * 8,
         "dmc_edge_adjoint": 3 * Vd * s,
     }

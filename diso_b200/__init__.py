@@ -74,9 +74,13 @@ class _Extract(Function):
         k = 3 if alg == _lib.ALG_MC else 4
         verts = torch.empty((n_verts, 3), dtype=grid.dtype, device=grid.device)
         faces = torch.empty((n_faces, k), dtype=torch.int64, device=grid.device)
-        emit = L.diso_b200_mc_emit if alg == _lib.ALG_MC else L.diso_b200_dmc_emit
-        _lib.check(emit(grid.data_ptr(), _ptr(deform), _DTYPES[grid.dtype], X, Y, Z, float(isovalue),
-                        state.data_ptr(), int(bool(normalize)), verts.data_ptr(), faces.data_ptr(), _stream()))
+        args = (grid.data_ptr(), _ptr(deform), _DTYPES[grid.dtype], X, Y, Z, float(isovalue), state.data_ptr(),
+                int(bool(normalize)))
+        if alg == _lib.ALG_MC:
+            _lib.check(L.diso_b200_mc_emit(*args, verts.data_ptr(), faces.data_ptr(), _stream()))
+        else:
+            scratch = torch.empty((max(n_faces, 1), 3), dtype=grid.dtype, device=grid.device)  # edge crossings
+            _lib.check(L.diso_b200_dmc_emit(*args, scratch.data_ptr(), verts.data_ptr(), faces.data_ptr(), _stream()))
         ctx.alg, ctx.isovalue, ctx.normalize, ctx.grad_mode = alg, float(isovalue), bool(normalize), grad_mode
         ctx.n_edges = n_verts if alg == _lib.ALG_MC else n_faces
         ctx.save_for_backward(grid, deform, state)

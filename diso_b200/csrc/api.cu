@@ -170,21 +170,21 @@ int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const 
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     const EpilogueC<T> epi = make_epilogue_c<T>(g, normalize);
     LAUNCH("mc_emit_verts", st, edge_verts_kernel<T><<<cdiv(g.NCH, CT_CHUNKS), CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, verts));
-    LAUNCH("mc_emit_tris", st, mc_emit_tris_kernel<<<grid, EMIT_WARPS * 32, 0, st>>>(g, p.S, p.E, reinterpret_cast<const unsigned *>(p.aux), tris));
+    LAUNCH("mc_emit_tris", st, mc_tris_kernel<<<cdiv(g.NCH, CT_CHUNKS), CT_THREADS, 0, st>>>(g, p.S, p.E, reinterpret_cast<const unsigned *>(p.aux), tris));
     return DISO_OK;
 }
 
 template <typename T>
-int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, int normalize, T *verts,
-                  long long *quads, cudaStream_t st)
+int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, int normalize, T *scratch,
+                  T *verts, long long *quads, cudaStream_t st)
 {
-    const int groups = cdiv(g.NCH, 32);
-    const int grid = cdiv(groups, EMIT_WARPS);
+    const int grid = cdiv(g.NCH, CT_CHUNKS);
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
-    const EpilogueC<T> epic = make_epilogue_c<T>(g, normalize);
-    LAUNCH("dmc_emit_verts", st, dmc_dual_verts_kernel<T><<<cdiv(g.NCH, CT_CHUNKS), CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epic, p.S, P, p.C, verts));
-    LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0><<<cdiv(g.NCH, CT_CHUNKS), CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, T(1), T(1), T(1), nullptr, quads, nullptr)));
+    const EpilogueC<T> raw = make_epilogue_c<T>(g, 0, false), epic = make_epilogue_c<T>(g, normalize);
+    LAUNCH("dmc_edge_crossings", st, edge_verts_kernel<T><<<grid, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, scratch));
+    LAUNCH("dmc_emit_verts", st, dmc_dual_verts_kernel<T><<<grid, CT_THREADS, 0, st>>>(scratch, g, epic, p.S, p.E, P, p.C, verts));
+    LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0><<<grid, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, T(1), T(1), T(1), nullptr, quads, nullptr)));
     return DISO_OK;
 }
 
@@ -316,19 +316,19 @@ int diso_b200_mc_emit(const void *sdf, const void *deform, int dtype, int X, int
 }
 
 int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
-                       const void *state, int normalize, void *verts, int64_t *quads, void *stream)
+                       const void *state, int normalize, void *scratch, void *verts, int64_t *quads, void *stream)
 {
     int rc = check_dims(DISO_ALG_DMC, dtype, X, Y, Z);
     if (rc) return rc;
-    if (!sdf || !state || !verts || !quads) return fail(DISO_E_INVALID, "null pointer");
+    if (!sdf || !state || !scratch || !verts || !quads) return fail(DISO_E_INVALID, "null pointer");
     const Geo g = make_geo(X, Y, Z);
     const StatePtrs p = state_ptrs(const_cast<void *>(state), make_layout(DISO_ALG_DMC, g));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == DISO_F32)
         return dmc_emit_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, normalize,
-                                    static_cast<float *>(verts), reinterpret_cast<long long *>(quads), st);
+                                    static_cast<float *>(scratch), static_cast<float *>(verts), reinterpret_cast<long long *>(quads), st);
     return dmc_emit_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, normalize,
-                                 static_cast<double *>(verts), reinterpret_cast<long long *>(quads), st);
+                                 static_cast<double *>(scratch), static_cast<double *>(verts), reinterpret_cast<long long *>(quads), st);
 }
 
 int diso_b200_mc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,

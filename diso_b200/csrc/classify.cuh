@@ -85,20 +85,27 @@ __global__ void __launch_bounds__(256) sign_pack_f32x4_kernel(const float *__res
     const float4 *rowp = reinterpret_cast<const float4 *>(sdf + ((size_t)(xp - 1) * g.Y + (yp - 1)) * g.Z);
     const int nvec = g.Z >> 2;
     bool any_gt = false;
-    for (int v0 = 0; v0 < nvec; v0 += 32) {
-        const int v = v0 + lane;
-        unsigned nib = 0xfu;  // beyond the row: ones (pad)
-        if (v < nvec) {
-            float4 q = __ldcs(rowp + v);
-            nib = (q.x >= iso ? 1u : 0u) | (q.y >= iso ? 2u : 0u) | (q.z >= iso ? 4u : 0u) | (q.w >= iso ? 8u : 0u);
-            any_gt |= (q.x > iso) | (q.y > iso) | (q.z > iso) | (q.w > iso);
+    for (int v0 = 0; v0 < nvec; v0 += 128) {
+        // up to four independent 128-bit loads in flight per lane (a 512-float row = one batch)
+        float4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int v = v0 + 32 * u + lane;
+            q[u] = make_float4(iso, iso, iso, iso);  // beyond the row: reads as "inside" (pad)
+            if (v < nvec) q[u] = __ldcs(rowp + v);
         }
-        unsigned w = nib << (4 * (lane & 7));
-        w |= __shfl_xor_sync(FULL, w, 1);
-        w |= __shfl_xor_sync(FULL, w, 2);
-        w |= __shfl_xor_sync(FULL, w, 4);
-        const int widx = (v0 >> 3) + (lane >> 3);  // aligned word index: 8 float4 per word
-        if ((lane & 7) == 0 && widx < NA) aw[widx] = w;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int v = v0 + 32 * u + lane;
+            unsigned nib = (q[u].x >= iso ? 1u : 0u) | (q[u].y >= iso ? 2u : 0u) | (q[u].z >= iso ? 4u : 0u) | (q[u].w >= iso ? 8u : 0u);
+            if (v < nvec) any_gt |= (q[u].x > iso) | (q[u].y > iso) | (q[u].z > iso) | (q[u].w > iso);
+            unsigned w = nib << (4 * (lane & 7));
+            w |= __shfl_xor_sync(FULL, w, 1);
+            w |= __shfl_xor_sync(FULL, w, 2);
+            w |= __shfl_xor_sync(FULL, w, 4);
+            const int widx = ((v0 + 32 * u) >> 3) + (lane >> 3);  // aligned word index: 8 float4 per word
+            if ((lane & 7) == 0 && widx < NA) aw[widx] = w;
+        }
     }
     __syncwarp();
     // padded word c covers z = 32c-1 .. 32c+30  ->  (aligned[c] << 1) | (aligned[c-1] >> 31)

@@ -13,6 +13,7 @@
 #pragma once
 #include "classify.cuh"
 #include "edge_math.cuh"
+#include "tables.cuh"
 
 namespace diso {
 
@@ -143,6 +144,110 @@ __global__ void __launch_bounds__(CT_THREADS) edge_verts_kernel(const T *__restr
         p = epi.apply(p);
         T *dst = verts + (size_t)(tile_base + i) * 3;
         st_stream(dst, p.x); st_stream(dst + 1, p.y); st_stream(dst + 2, p.z);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Edge-record cache: the records of the four rows a cell's 12 edges are owned by
+// (rowset = 2*dx + dy of mcEdgeLocations, cumc.cu:109-122), for the tile's chunks plus the
+// following one (dz = 1 from lane 31).  Filled with coalesced 16-byte loads in phase A so that
+// phase B turns "edge id -> vertex id" into one LDS.128 + three popcounts -- the reference does
+// an owner-cell lookup, two offset loads and a linear search per index (cumc.cu:589-607).
+// ------------------------------------------------------------------------------------------
+constexpr int CT_REC = CT_CHUNKS + 2;
+
+__device__ __forceinline__ void load_record_cache(const Geo &g, const uint4 *__restrict__ E, int k0, uint4 (*s_E)[CT_REC])
+{
+    for (int i = threadIdx.x; i < 4 * (CT_CHUNKS + 1); i += CT_THREADS) {
+        const int rs = i / (CT_CHUNKS + 1), cl = i - rs * (CT_CHUNKS + 1);
+        const int kk = k0 + cl + (rs >> 1) * g.sX + (rs & 1) * g.sY;   // E has a zero-filled tail of sX+sY+8 records
+        s_E[rs][cl] = (k0 + cl <= g.NCH) ? __ldg(E + kk) : make_uint4(0, 0, 0, 0);
+    }
+}
+
+// vertex id of local edge e of cell (chunk-in-tile cl, lane j)
+__device__ __forceinline__ unsigned edge_rank(const uint4 (*s_E)[CT_REC], int cl, int j, int e)
+{
+    const int ax = (EDGE_AX >> (2 * e)) & 3;
+    const int rs = (((EDGE_DX >> e) & 1) << 1) | ((EDGE_DY >> e) & 1);
+    int jj = j + ((EDGE_DZ >> e) & 1);
+    if (jj == 32) { cl += 1; jj = 0; }
+    const uint4 rec = s_E[rs][cl];
+    const unsigned l = lanemask_lt(jj);
+    unsigned r = rec.x + __popc(rec.y & l) + __popc(rec.z & l) + __popc(rec.w & l);
+    if (ax >= 1) r += bit(rec.y, jj);
+    if (ax == 2) r += bit(rec.z, jj);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4 (v2): triangles, triangle-parallel.  Replaces count_cell_mc_tris / create_cell_mc_tris
+// (cumc.cu:540-612) + the int64 widening (diso/__init__.py:61).
+//   phase A  lane == cell: case index from the sign words, triangle count from the packed case
+//            table, warp prefix -> one descriptor {chunk-in-tile, lane, k-th triangle} per
+//            triangle at slot (triangle id - first triangle id of the tile).
+//   phase B  thread == triangle: three edge ids from the case table -> three vertex ids via the
+//            record cache -> 24 contiguous bytes at the triangle's output rank.
+// ------------------------------------------------------------------------------------------
+constexpr int CT_MAX_TRIS = CT_CHUNKS * 160;
+
+__global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const unsigned *__restrict__ S, const uint4 *__restrict__ E,
+                                                           const unsigned *__restrict__ F, long long *__restrict__ tris)
+{
+    __shared__ unsigned long long s_case[256];
+    __shared__ uint4 s_E[4][CT_REC];
+    __shared__ unsigned short s_list[CT_MAX_TRIS];
+    __shared__ unsigned char s_code[CT_CHUNKS * 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int k0 = blockIdx.x * CT_CHUNKS;
+    const int kend = min(k0 + CT_CHUNKS, g.NCH);
+    const unsigned tile_base = F[k0];
+    const unsigned n = F[kend] - tile_base;
+    if (n == 0) return;
+    s_case[threadIdx.x] = T_MC_CASE[threadIdx.x];
+    load_record_cache(g, E, k0, s_E);
+    __syncthreads();
+
+    constexpr int PER_WARP = CT_CHUNKS / CT_WARPS;
+    {
+        const int kmine = k0 + wid * PER_WARP + lane;
+        unsigned f_lo = 0, f_hi = 0;
+        if (lane < PER_WARP && kmine < kend) { f_lo = F[kmine]; f_hi = F[kmine + 1]; }
+        unsigned active = __ballot_sync(FULL, f_hi != f_lo);
+        while (active) {
+            const int i = __ffs(active) - 1;
+            active &= active - 1;
+            const int cl = wid * PER_WARP + i;
+            const unsigned tb = __shfl_sync(FULL, f_lo, i) - tile_base;
+            const CellWords w = load_cell_words(S, g, k0 + cl);
+            const unsigned used = used_mask(w);
+            const unsigned code = bit(used, lane) ? cell_code<DISO_ALG_MC>(w, lane) : 0u;
+            s_code[cl * 32 + lane] = (unsigned char)code;
+            const unsigned nt = (unsigned)(s_case[code] >> 60);
+            unsigned incl = nt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned t = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const unsigned slot = tb + incl - nt;
+#pragma unroll
+            for (unsigned q = 0; q < 5; ++q)
+                if (q < nt) s_list[slot + q] = (unsigned short)((cl << 8) | (lane << 3) | q);
+        }
+    }
+    __syncthreads();
+
+    for (unsigned i = threadIdx.x; i < n; i += CT_THREADS) {
+        const unsigned d = s_list[i];
+        const unsigned q = d & 7u;
+        const int j = (d >> 3) & 31, cl = (d >> 8) & 63;
+        const unsigned tri = (unsigned)(s_case[s_code[cl * 32 + j]] >> (12 * q)) & 0xfffu;
+        const long long a = edge_rank(s_E, cl, j, tri & 15u);
+        const long long b = edge_rank(s_E, cl, j, (tri >> 4) & 15u);
+        const long long c = edge_rank(s_E, cl, j, tri >> 8);
+        long long *dst = tris + (size_t)(tile_base + i) * 3;
+        st_stream(dst, a); st_stream(dst + 1, b); st_stream(dst + 2, c);
     }
 }
 

@@ -88,26 +88,31 @@ constexpr int CT_MAX_PATCHES = CT_CHUNKS * 128;
 // ------------------------------------------------------------------------------------------
 // K3d (v2): dual vertices, patch-parallel.  Replaces create_dmc_verts_kernel
 // (cudualmc.cu:907-955) + epilogue (diso/__init__.py:110-114).
+// The reference recomputes every edge crossing on the fly in each of the 4 cells around the
+// edge (cudualmc.cu:946-948).  Here the crossings are evaluated ONCE by edge_verts_kernel in
+// the raw padded frame into `mcv` (caller scratch, [n_edges,3]) and this kernel only averages:
 //   phase A  lane == cell: (possibly complemented) case index, patch count and first-dual-
 //            vertex id of every cell of the tile's active chunks -> per-cell array C (global,
 //            consumed by the quad / adjoint kernels) + one descriptor per patch in the shared
 //            list at slot (dual vertex id - first id of the tile).
-//   phase B  thread == dual vertex: sum the crossings of the patch's member edges in ascending
-//            edge id (== the reference's table order, asserted in tools/extract_tables.py),
-//            scale by 1/len, apply the epilogue, store at consecutive output ranks.
+//   phase B  thread == dual vertex: gather the crossings of the patch's member edges by rank in
+//            ascending edge id (== the reference's table order, asserted in
+//            tools/extract_tables.py), sum, scale by 1/len, apply the epilogue, store at
+//            consecutive output ranks.  Same values in the same order => bit-identical.
 // ------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(CT_THREADS) dmc_dual_verts_kernel(const T *__restrict__ sdf, const T *__restrict__ deform,
-                                                                  Geo g, T iso, T padv, EpilogueC<T> epi,
+__global__ void __launch_bounds__(CT_THREADS) dmc_dual_verts_kernel(const T *__restrict__ mcv, Geo g, EpilogueC<T> epi,
                                                                   const unsigned *__restrict__ S,
+                                                                  const uint4 *__restrict__ E,
                                                                   const uint4 *__restrict__ P,
                                                                   unsigned short *__restrict__ C, T *__restrict__ verts)
 {
     __shared__ unsigned short s_list[CT_MAX_PATCHES];
     __shared__ unsigned short s_cell[CT_CHUNKS * 32];
-    __shared__ TilePos s_pos[CT_CHUNKS];
     __shared__ unsigned s_case[256];
     __shared__ unsigned s_plen[256];
+    __shared__ unsigned long long s_members[256];
+    __shared__ uint4 s_E[4][CT_REC];
     __shared__ T s_inv[8];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int k0 = blockIdx.x * CT_CHUNKS;
@@ -117,6 +122,8 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_dual_verts_kernel(const T *__r
     if (n == 0) return;
     s_case[threadIdx.x] = T_DMC_CASE[threadIdx.x];
     s_plen[threadIdx.x] = T_DMC_PATCHLEN[threadIdx.x];
+    s_members[threadIdx.x] = T_DMC_MEMBERS[threadIdx.x];
+    load_record_cache(g, E, k0, s_E);
     if (threadIdx.x < 8) s_inv[threadIdx.x] = threadIdx.x ? T(1) / T((int)threadIdx.x) : T(0);
     __syncthreads();
 
@@ -125,16 +132,7 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_dual_verts_kernel(const T *__r
     {
         const int kmine = k0 + wid * PER_WARP + lane;
         bool act = false;
-        if (lane < PER_WARP && kmine < kend) {
-            act = P[kmine + 1].x != P[kmine].x;
-            const int r = kmine / g.NC;
-            TilePos tp;
-            tp.c = (short)(kmine - r * g.NC);
-            tp.xp = (short)(r / g.PY);
-            tp.yp = (short)(r - (r / g.PY) * g.PY);
-            tp.pad = 0;
-            s_pos[wid * PER_WARP + lane] = tp;
-        }
+        if (lane < PER_WARP && kmine < kend) act = P[kmine + 1].x != P[kmine].x;
         unsigned active = __ballot_sync(FULL, act);
         while (active) {
             const int i = __ffs(active) - 1;
@@ -154,35 +152,39 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_dual_verts_kernel(const T *__r
     __syncthreads();
 
     // ---- phase B ---------------------------------------------------------------------------------
-    const bool has_def = deform != nullptr;
     for (unsigned i = threadIdx.x; i < n; i += CT_THREADS) {
         const unsigned d = s_list[i];
         const unsigned q = d & 3u;
         const int j = (d >> 2) & 31, cl = (d >> 7) & 63;
-        const TilePos tp = s_pos[cl];
-        const int xp = tp.xp, yp = tp.yp, zp = 32 * tp.c + j;
         const unsigned code = s_cell[cl * 32 + j] & 0xffu;
-        const unsigned ce = s_case[code], plen = s_plen[code];
-        Vec3<T> acc{T(0), T(0), T(0)};
-        for (unsigned m = plen >> 16; m; m &= m - 1) {  // crossing edges of the case, ascending id
-            const int e = __ffs(m) - 1;
-            if (((ce >> (2 * e)) & 3u) != q) continue;
-            const int ax = (EDGE_AX >> (2 * e)) & 3;
-            const int x0 = xp + ((EDGE_DX >> e) & 1), y0 = yp + ((EDGE_DY >> e) & 1), z0 = zp + ((EDGE_DZ >> e) & 1);
-            const int x1 = x0 + (ax == 0), y1 = y0 + (ax == 1), z1 = z0 + (ax == 2);
-            const T d0 = fetch_padded(sdf, g, x0, y0, z0, padv);
-            const T d1 = fetch_padded(sdf, g, x1, y1, z1, padv);
-            const T t = edge_t(d0, d1, iso);
-            Vec3<T> p0{T(x0), T(y0), T(z0)}, p1{T(x1), T(y1), T(z1)};
-            if (has_def) {
-                const Vec3<T> f0 = fetch_deform(deform, g, x0, y0, z0), f1 = fetch_deform(deform, g, x1, y1, z1);
-                p0.x = p0.x + f0.x; p0.y = p0.y + f0.y; p0.z = p0.z + f0.z;
-                p1.x = p1.x + f1.x; p1.y = p1.y + f1.y; p1.z = p1.z + f1.z;
+        const unsigned plen = s_plen[code];
+        unsigned mm = (unsigned)(s_members[code] >> (12 * q)) & 0xfffu;  // member edges of this patch
+        // pass 1: ranks of the (<= 7) member edges, ascending edge id
+        unsigned rank[7];
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+            rank[t] = 0xffffffffu;
+            if (mm) {
+                const int e = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const unsigned r = edge_rank(s_E, cl, j, e);
+                rank[t] = r;
             }
-            acc.x = acc.x + fma_rn(p1.x - p0.x, t, p0.x);
-            acc.y = acc.y + fma_rn(p1.y - p0.y, t, p0.y);
-            acc.z = acc.z + fma_rn(p1.z - p0.z, t, p0.z);
         }
+        // pass 2: gather + sum in the same (ascending edge id) order
+        T vx[7], vy[7], vz[7];
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+            vx[t] = vy[t] = vz[t] = T(0);
+            if (rank[t] != 0xffffffffu) {
+                const T *pv = mcv + (size_t)rank[t] * 3;
+                vx[t] = __ldg(pv); vy[t] = __ldg(pv + 1); vz[t] = __ldg(pv + 2);
+            }
+        }
+        Vec3<T> acc{T(0), T(0), T(0)};
+#pragma unroll
+        for (int t = 0; t < 7; ++t)
+            if (rank[t] != 0xffffffffu) { acc.x = acc.x + vx[t]; acc.y = acc.y + vy[t]; acc.z = acc.z + vz[t]; }
         const T inv = s_inv[(plen >> (4 * q)) & 7u];
         Vec3<T> v{acc.x * inv, acc.y * inv, acc.z * inv};
         v = epi.apply(v);

@@ -83,9 +83,11 @@ int diso_b200_mc_emit(const void *sdf, const void *deform, int dtype, int X, int
 
 /* Phase 2, dual marching cubes (replaces create_dmc_verts / create_quads,
  * cudualmc.cu:907-955, 1027-1056, and diso/__init__.py:110-116).
- * verts: [n_verts,3] dtype; quads: [n_quads,4] int64. */
+ * verts: [n_verts,3] dtype; quads: [n_quads,4] int64.
+ * scratch: caller-owned, n_quads*3 elements of dtype (edge crossings, each evaluated once).
+ * This call also completes `state` with the per-cell array diso_b200_dmc_backward needs. */
 int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
-                       double iso, const void *state, int normalize, void *verts,
+                       double iso, const void *state, int normalize, void *scratch, void *verts,
                        int64_t *quads, void *stream);
 
 /* Backward, marching cubes (replaces adj_create_cell_mc_verts, cumc.cu:474-512, the dense

@@ -62,6 +62,10 @@ def test_packed_kernel_tables_consistent_with_oracle_tables():
                 assert (w >> (2 * e)) & 3 == o
         for p in range(npatch):
             assert (c >> (4 * p)) & 15 == ef[pf[code] + p + 1] - ef[pf[code] + p]
+        mem = k["T_DMC_MEMBERS"][code]
+        for q in range(4):
+            want_m = sum(1 << e for e in range(12) if off[code * 12 + e] == q)
+            assert (mem >> (12 * q)) & 0xfff == want_m
         assert (w >> 31) == (prob[code] != 255)
         if prob[code] != 255:
             assert (w >> 28) & 7 == prob[code]

@@ -226,6 +226,19 @@ def main():
     for i in range(0, 256, 8):
         inc.append("    " + ", ".join("0x%08xu" % v for v in dmc_cnt[i:i + 8]) + ",")
     inc.append("};")
+    # per case: four 12-bit masks (bits 12q..12q+11) = member edges of patch q
+    members = []
+    for code in range(256):
+        w = 0
+        for e in range(12):
+            o = off[code * 12 + e]
+            if o >= 0:
+                w |= 1 << (12 * o + e)
+        members.append(w)
+    inc.append("DISO_TABLE_QUAL unsigned long long T_DMC_MEMBERS[256] = {")
+    for i in range(0, 256, 4):
+        inc.append("    " + ", ".join("0x%012xull" % v for v in members[i:i + 4]) + ",")
+    inc.append("};")
     inc.append("DISO_TABLE_QUAL unsigned int T_DMC_QUAD[6] = {" + ", ".join("0x%08xu" % v for v in quad_pack) + "};")
     inc.append("")
     with open(os.path.join(ROOT, "diso_b200/csrc/case_tables.inc"), "w") as f:
