@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <string>
@@ -100,6 +101,14 @@ template <typename T> EpilogueC<T> make_epilogue_c(const Geo &g, int normalize, 
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+inline int sm_count()
+{
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+        n = 148;  // B200
+    return n;
+}
+
 // ---- tracing: launch counter + optional per-kernel CUDA-event timing (per host thread) --------
 std::atomic<long long> g_launches{0};
 struct ProfRec { const char *name; cudaEvent_t a, b; };
@@ -149,7 +158,8 @@ int count_impl(int alg, const T *sdf, const Geo &g, double iso, const StateLayou
     if (vec4) {
         const int NA = (g.Z + 31) / 32;
         const size_t smem = (size_t)warps * (NA + 2) * 4;
-        LAUNCH("sign_pack_f32x4", st, sign_pack_f32x4_kernel<<<cdiv(g.NR, warps), warps * 32, smem, st>>>(
+        const int ctas = std::min(cdiv(g.NR, warps), sm_count() * 6);  // persistent: warps stride over the rows
+        LAUNCH("sign_pack_f32x4", st, sign_pack_f32x4_kernel<<<ctas, warps * 32, smem, st>>>(
                                           reinterpret_cast<const float *>(sdf), g, (float)isoT, p.S, p.counts));
     } else {
         LAUNCH("sign_pack", st, sign_pack_kernel<T><<<cdiv(g.NR, warps), warps * 32, 0, st>>>(sdf, g, isoT, p.S, p.counts));
