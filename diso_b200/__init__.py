@@ -14,7 +14,7 @@ from torch.autograd import Function
 from . import _lib
 from ._lib import DisoB200Error  # noqa: F401
 
-__all__ = ["DiffMC", "DiffDMC", "extract_counts", "debug_cell_codes", "split_quads"]
+__all__ = ["DiffMC", "DiffDMC", "extract_counts", "debug_cell_codes", "split_quads", "layer_prefixes"]
 __version__ = "0.1.0"
 
 _DTYPES = {torch.float32: _lib.F32, torch.float64: _lib.F64}
@@ -116,7 +116,7 @@ class _Extract(Function):
         return adj_grid, adj_deform, None, None, None, None, None, None, None
 
 
-def _run(alg, dtype, grad_mode, grid, deform, isovalue, normalize):
+def _run(alg, dtype, grad_mode, grid, deform, isovalue, normalize, want_state=False, slab_mode=False):
     _check_inputs(grid, deform, dtype)
     k = 3 if alg == _lib.ALG_MC else 4
     with torch.cuda.device(grid.device):
@@ -127,12 +127,38 @@ def _run(alg, dtype, grad_mode, grid, deform, isovalue, normalize):
         n_verts, n_faces = counts[_lib.CNT_VERTS], counts[_lib.CNT_FACES]
         # diso/__init__.py:49-50,103-104: empty-surface early-out (min >= iso or max <= iso),
         # which returns detached (0,3) verts and INT32 (0,3)/(0,4) faces.
-        if counts[_lib.CNT_EDGES] == 0 or counts[_lib.CNT_ANY_GT] == 0:
-            return (torch.zeros((0, 3), dtype=dtype, device=grid.device),
-                    torch.zeros((0, k), dtype=torch.int32, device=grid.device))
+        # (slab_mode: the "max <= iso" half of the test is a property of the GLOBAL grid, decided by the caller)
+        if counts[_lib.CNT_EDGES] == 0 or (counts[_lib.CNT_ANY_GT] == 0 and not slab_mode):
+            out = (torch.zeros((0, 3), dtype=dtype, device=grid.device),
+                   torch.zeros((0, k), dtype=torch.int32, device=grid.device))
+            return out + (None,) if want_state else out
         if max(n_verts, n_faces) >= 2 ** 32 - 1:
             raise DisoB200Error("mesh too large for one call (%d verts, %d faces): shard the grid" % (n_verts, n_faces))
-        return _Extract.apply(g, d, alg, float(isovalue), bool(normalize), grad_mode, state, n_verts, n_faces)
+        out = _Extract.apply(g, d, alg, float(isovalue), bool(normalize), grad_mode, state, n_verts, n_faces)
+        return out + (state,) if want_state else out
+
+
+def layer_prefixes(alg, state, shape):
+    """Per padded x-layer exclusive prefix sums read from a state tensor (host int64 tensors of
+    length X+3): number of crossing edges (== MC vertices == DMC quads) and of MC triangles /
+    DMC dual vertices owned by all layers before layer xp.  All output orderings are ascending
+    in x, so the items owned by layers [a, b) are the contiguous ranges prefix[a]:prefix[b]."""
+    import ctypes
+    L = _lib.load()
+    alg_id = {"mc": _lib.ALG_MC, "dmc": _lib.ALG_DMC}.get(alg, alg)
+    X, Y, Z = shape
+    lay = (ctypes.c_int64 * 8)()
+    _lib.check(L.diso_b200_state_layout(alg_id, X, Y, Z, lay))
+    off_e, off_aux, nch, sx = lay[1], lay[2], lay[5], lay[7]
+    idx = torch.arange(0, X + 3, device=state.device, dtype=torch.int64) * sx  # layer starts; last == NCH (totals)
+    words = state.view(torch.int32)
+    e = words[off_e // 4 + idx * 4].to(torch.int64) & 0xffffffff
+    if alg_id == _lib.ALG_MC:
+        f = words[off_aux // 4 + idx].to(torch.int64) & 0xffffffff
+    else:
+        f = words[off_aux // 4 + idx * 4].to(torch.int64) & 0xffffffff
+    assert int(idx[-1]) == nch
+    return e.cpu(), f.cpu()
 
 
 def _grad_mode(name):

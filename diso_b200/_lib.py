@@ -22,6 +22,7 @@ SIGNATURES = {
     "diso_b200_abi_version": (_i, []),
     "diso_b200_last_error": (ctypes.c_char_p, []),
     "diso_b200_state_bytes": (_sz, [_i, _i, _i, _i]),
+    "diso_b200_state_layout": (_i, [_i, _i, _i, _i, ctypes.POINTER(ctypes.c_int64)]),
     "diso_b200_count": (_i, [_i, _vp, _i, _i, _i, _i, _d, _vp, _sz, _vp]),
     "diso_b200_mc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _i, _vp, _vp, _vp]),
     "diso_b200_dmc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _i, _vp, _vp, _vp, _vp]),

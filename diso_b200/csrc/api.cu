@@ -293,6 +293,18 @@ size_t diso_b200_state_bytes(int alg, int X, int Y, int Z)
     return make_layout(alg, make_geo(X, Y, Z)).total;
 }
 
+int diso_b200_state_layout(int alg, int X, int Y, int Z, int64_t *out)
+{
+    int rc = check_dims(alg, DISO_F32, X, Y, Z);
+    if (rc) return rc;
+    if (!out) return fail(DISO_E_INVALID, "null pointer");
+    const Geo g = make_geo(X, Y, Z);
+    const StateLayout L = make_layout(alg, g);
+    out[0] = (int64_t)L.off_sign; out[1] = (int64_t)L.off_erec; out[2] = (int64_t)L.off_aux; out[3] = (int64_t)L.off_cell;
+    out[4] = g.NC; out[5] = g.NCH; out[6] = (int64_t)L.total; out[7] = g.sX;
+    return DISO_OK;
+}
+
 int diso_b200_count(int alg, const void *sdf, int dtype, int X, int Y, int Z, double iso, void *state,
                     size_t state_bytes, void *stream)
 {

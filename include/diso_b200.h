@@ -66,6 +66,13 @@ const char *diso_b200_last_error(void);
  * (sign bitmask + per-32-point records) that emit/backward consume.  Returns 0 on bad args. */
 size_t diso_b200_state_bytes(int alg, int X, int Y, int Z);
 
+/* Byte offsets of the arrays inside `state`, for hosts that want to
+ * read the per-chunk prefix sums (slab sharding, diso_b200/parallel.py):
+ * out[0..3] = offsets of S (u32), E (uint4), F (u32, MC) | P (uint4, DMC), C (u16, DMC);
+ * out[4] = NC (chunks per padded row), out[5] = NCH (chunks), out[6] = total bytes,
+ * out[7] = chunks per padded x-layer.  Entry NCH of E / F / P holds the grand totals. */
+int diso_b200_state_layout(int alg, int X, int Y, int Z, int64_t *out);
+
 /* Phase 1 (replaces count_used_cells / index_used_cells / count_cell_mc_verts /
  * count_cell_mc_tris|count_cell_patches and the three cub scans, cumc.cu:661-723,
  * cudualmc.cu:1068-1122): classify every cell, count vertices / faces, build the rank
