@@ -154,7 +154,7 @@ def layer_prefixes(alg, state, shape):
     words = state.view(torch.int32)
     e = words[off_e // 4 + idx * 4].to(torch.int64) & 0xffffffff
     if alg_id == _lib.ALG_MC:
-        f = words[off_aux // 4 + idx].to(torch.int64) & 0xffffffff
+        f = words[off_aux // 4 + idx * 2].to(torch.int64) & 0xffffffff
     else:
         f = words[off_aux // 4 + idx * 4].to(torch.int64) & 0xffffffff
     assert int(idx[-1]) == nch

@@ -211,6 +211,7 @@ __device__ __forceinline__ bool dmc_flip(const unsigned *__restrict__ S, const G
 template <int ALG>
 __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const unsigned *__restrict__ S,
                                                                   uint4 *__restrict__ E, void *__restrict__ aux,
+                                                                  unsigned short *__restrict__ C,
                                                                   TileDesc *__restrict__ desc,
                                                                   unsigned *__restrict__ ticket,
                                                                   long long *__restrict__ counts)
@@ -220,8 +221,14 @@ __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const u
     __shared__ unsigned s_warp_tot[SCAN_TILE / 32];
     __shared__ unsigned long long s_excl[2];
     __shared__ unsigned s_used_tot;
+    // per-cell words of the tile, staged so they leave the SM as coalesced stores: row stride of 17
+    // words keeps the per-thread 2-byte writes of one warp in 32 distinct banks
+    constexpr int CW_STRIDE = 17;
+    __shared__ unsigned s_cw[SCAN_TILE * CW_STRIDE];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < CW_STRIDE; ++i) s_cw[i * SCAN_TILE + tid] = 0u;
     if (ALG == DISO_ALG_MC) s_tab[tid] = (unsigned)(T_MC_CASE[tid] >> 60);
     else                    s_tab[tid] = T_DMC_CASE[tid];
     if (tid == 0) { s_tile = atomicAdd(ticket, 1u); s_used_tot = 0; }
@@ -229,7 +236,7 @@ __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const u
     const int tile = (int)s_tile;
     const int k = tile * SCAN_TILE + tid;
 
-    unsigned mx = 0, my = 0, mz = 0, lo = 0, hi = 0, flip = 0;
+    unsigned mx = 0, my = 0, mz = 0, lo = 0, hi = 0, used = 0;
     unsigned na = 0, nb = 0, nused = 0;
     if (k < g.NCH) {
         CellWords w = load_cell_words(S, g, k);
@@ -237,20 +244,23 @@ __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const u
         my = w.A ^ w.D;
         mz = w.A ^ w.A1;
         na = __popc(mx) + __popc(my) + __popc(mz);
-        unsigned used = used_mask(w);
+        used = used_mask(w);
         nused = __popc(used);
         if (used) {
             int r = k / g.NC, c = k - r * g.NC;
             int xp = r / g.PY, yp = r - xp * g.PY;
+            unsigned short *crow = reinterpret_cast<unsigned short *>(s_cw + tid * CW_STRIDE);
             unsigned u = used;
-            while (u) {
+            while (u) {  // ascending j: nb is the cell's offset inside the chunk
                 int j = __ffs(u) - 1;
                 u &= u - 1;
                 unsigned code = cell_code<ALG>(w, j);
                 if (ALG == DISO_ALG_MC) {
+                    crow[j] = (unsigned short)(code | (nb << 8));
                     nb += s_tab[code];
                 } else {
-                    if (dmc_flip(S, g, s_tab, k, xp, yp, c, j, code)) { code ^= 0xffu; flip |= 1u << j; }
+                    if (dmc_flip(S, g, s_tab, k, xp, yp, c, j, code)) code ^= 0xffu;
+                    crow[j] = (unsigned short)(code | (nb << 8));
                     unsigned np = (s_tab[code] >> 24) & 7u;  // 1..4
                     nb += np;
                     lo |= ((np - 1u) & 1u) << j;
@@ -333,19 +343,44 @@ __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const u
     const unsigned long long base_a = s_excl[0] + (excl_local & 0xffffu);
     const unsigned long long base_b = s_excl[1] + (excl_local >> 16);
 
+    // flush the staged per-cell words: 16 words (32 cells) per chunk, coalesced
+    {
+        unsigned *cout = reinterpret_cast<unsigned *>(C) + (size_t)tile * SCAN_TILE * 16;
+        const int rows = min(SCAN_TILE, g.NCH - tile * SCAN_TILE);
+        for (int i = tid; i < rows * 16; i += SCAN_TILE) cout[i] = s_cw[(i >> 4) * CW_STRIDE + (i & 15)];
+    }
     if (k < g.NCH) {
         E[k] = make_uint4((unsigned)base_a, mx, my, mz);
-        if (ALG == DISO_ALG_MC) reinterpret_cast<unsigned *>(aux)[k] = (unsigned)base_b;
-        else reinterpret_cast<uint4 *>(aux)[k] = make_uint4((unsigned)base_b, lo, hi, flip);
+        if (ALG == DISO_ALG_MC) reinterpret_cast<uint2 *>(aux)[k] = make_uint2((unsigned)base_b, used);
+        else reinterpret_cast<uint4 *>(aux)[k] = make_uint4((unsigned)base_b, used, lo, hi);
     } else if (k == g.NCH) {
         // slot NCH: totals (also the sentinel "next chunk" of the last real chunk)
         E[k] = make_uint4((unsigned)base_a, 0u, 0u, 0u);
-        if (ALG == DISO_ALG_MC) reinterpret_cast<unsigned *>(aux)[k] = (unsigned)base_b;
+        if (ALG == DISO_ALG_MC) reinterpret_cast<uint2 *>(aux)[k] = make_uint2((unsigned)base_b, 0u);
         else reinterpret_cast<uint4 *>(aux)[k] = make_uint4((unsigned)base_b, 0u, 0u, 0u);
         counts[DISO_CNT_EDGES] = (long long)base_a;
         if (ALG == DISO_ALG_MC) { counts[DISO_CNT_VERTS] = (long long)base_a; counts[DISO_CNT_FACES] = (long long)base_b; }
         else                    { counts[DISO_CNT_VERTS] = (long long)base_b; counts[DISO_CNT_FACES] = (long long)base_a; }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Diagnostics: dense per-cell case index (see diso_b200_debug_cell_codes in the header).
+// ------------------------------------------------------------------------------------------
+template <int ALG>
+__global__ void debug_codes_kernel(Geo g, const unsigned *__restrict__ S, const unsigned short *__restrict__ C,
+                                   unsigned char *__restrict__ codes)
+{
+    const long long n = (long long)g.PX * g.PY * g.PZ;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int zp = (int)(idx % g.PZ);
+    const long long r = idx / g.PZ;
+    const int k = (int)(r * g.NC + (zp >> 5)), j = zp & 31;
+    const CellWords w = load_cell_words(S, g, k);
+    unsigned code = cell_code<ALG>(w, j);                       // unused cells: 0 or 255
+    if (bit(used_mask(w), j)) code = C[(size_t)k * 32 + j] & 0xffu;  // used cells: the stored (DMC: flipped) case
+    codes[idx] = (unsigned char)code;
 }
 
 }  // namespace diso

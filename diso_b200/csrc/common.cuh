@@ -14,13 +14,14 @@
 //                         point j crosses the iso level; base = number of crossing edges
 //                         owned by all points before chunk k (== id of the first MC vertex /
 //                         DMC quad of the chunk, reference order: point-major, axis-minor).
-//   * MC  : F[k]        : id of the first triangle emitted by the cells of chunk k.
-//   * DMC : P[k]        : {base, lo, hi, flip}: base = id of the first dual vertex of the
-//                         chunk; (lo,hi) bit j = (patch count - 1) of cell j; flip bit j = the
-//                         cell's case index is complemented (cudualmc.cu:815-839).
-//           C[32k + j]  : per used cell, 16 bits: (possibly complemented) case index | (id of the
-//                         cell's first dual vertex - P[k].base) << 8; written by the dual-vertex
-//                         kernel of diso_b200_dmc_emit, read by the quad / adjoint kernels.
+//   * MC  : F[k]        : {base, used}: id of the first triangle emitted by the cells of chunk
+//                         k; used bit j = cell j is a used cell.
+//   * DMC : P[k]        : {base, used, lo, hi}: base = id of the first dual vertex of the
+//                         chunk; (lo,hi) bit j = (patch count - 1) of cell j.
+//   * C[32k + j]        : per USED cell, 16 bits: case index (DMC: after the ambiguity flip,
+//                         cudualmc.cu:815-839) | (id of the cell's first triangle / dual vertex
+//                         - base of its chunk) << 8.  Entries of unused cells are never written
+//                         nor read (consumers mask with `used`).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -71,8 +72,8 @@ struct StateLayout {
     size_t off_desc;     // TileDesc[n_tiles]
     size_t off_sign;     // u32[NCH + sign_tail]
     size_t off_erec;     // uint4[NCH + rec_tail]
-    size_t off_aux;      // MC: u32 F[NCH+1] (padded to 16 B) ; DMC: uint4 P[NCH + rec_tail]
-    size_t off_cell;     // DMC only: u16 C[(NCH + 8) * 32] per-cell {case index | first-dual-vertex offset << 8}
+    size_t off_aux;      // MC: uint2 F[NCH + 8] ; DMC: uint4 P[NCH + rec_tail]
+    size_t off_cell;     // u16 C[(NCH + 8) * 32] per-cell {case index | offset of first triangle / dual vertex << 8}
     size_t total;
     int n_tiles;
     int sign_tail;
@@ -97,11 +98,11 @@ inline StateLayout make_layout(int alg, const Geo &g)
     L.off_erec = o;   o += ((size_t)g.NCH + L.rec_tail) * 16;
     o = align_up(o, 256);
     L.off_aux = o;
-    if (alg == DISO_ALG_MC) o += ((size_t)g.NCH + 8) * 4;
+    if (alg == DISO_ALG_MC) o += ((size_t)g.NCH + 8) * 8;
     else                    o += ((size_t)g.NCH + L.rec_tail) * 16;
     o = align_up(o, 256);
     L.off_cell = o;
-    if (alg == DISO_ALG_DMC) o += ((size_t)g.NCH + 8) * 32 * 2;
+    o += ((size_t)g.NCH + 8) * 32 * 2;
     L.total = align_up(o, 256);
     return L;
 }

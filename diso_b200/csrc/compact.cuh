@@ -183,16 +183,16 @@ __device__ __forceinline__ unsigned edge_rank(const uint4 (*s_E)[CT_REC], int cl
 // ------------------------------------------------------------------------------------------
 // K4 (v2): triangles, triangle-parallel.  Replaces count_cell_mc_tris / create_cell_mc_tris
 // (cumc.cu:540-612) + the int64 widening (diso/__init__.py:61).
-//   phase A  lane == cell: case index from the sign words, triangle count from the packed case
-//            table, warp prefix -> one descriptor {chunk-in-tile, lane, k-th triangle} per
+//   phase A  lane == cell: the per-cell word written by classify_scan (case index | offset of the
+//            cell's first triangle) -> one descriptor {chunk-in-tile, lane, k-th triangle} per
 //            triangle at slot (triangle id - first triangle id of the tile).
 //   phase B  thread == triangle: three edge ids from the case table -> three vertex ids via the
 //            record cache -> 24 contiguous bytes at the triangle's output rank.
 // ------------------------------------------------------------------------------------------
 constexpr int CT_MAX_TRIS = CT_CHUNKS * 160;
 
-__global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const unsigned *__restrict__ S, const uint4 *__restrict__ E,
-                                                           const unsigned *__restrict__ F, long long *__restrict__ tris)
+__global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const uint4 *__restrict__ E, const uint2 *__restrict__ F,
+                                                           const unsigned short *__restrict__ C, long long *__restrict__ tris)
 {
     __shared__ unsigned long long s_case[256];
     __shared__ uint4 s_E[4][CT_REC];
@@ -201,8 +201,8 @@ __global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const unsign
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int k0 = blockIdx.x * CT_CHUNKS;
     const int kend = min(k0 + CT_CHUNKS, g.NCH);
-    const unsigned tile_base = F[k0];
-    const unsigned n = F[kend] - tile_base;
+    const unsigned tile_base = F[k0].x;
+    const unsigned n = F[kend].x - tile_base;
     if (n == 0) return;
     s_case[threadIdx.x] = T_MC_CASE[threadIdx.x];
     load_record_cache(g, E, k0, s_E);
@@ -211,26 +211,21 @@ __global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const unsign
     constexpr int PER_WARP = CT_CHUNKS / CT_WARPS;
     {
         const int kmine = k0 + wid * PER_WARP + lane;
-        unsigned f_lo = 0, f_hi = 0;
-        if (lane < PER_WARP && kmine < kend) { f_lo = F[kmine]; f_hi = F[kmine + 1]; }
-        unsigned active = __ballot_sync(FULL, f_hi != f_lo);
+        uint2 f = make_uint2(0, 0);
+        if (lane < PER_WARP && kmine < kend) f = F[kmine];
+        unsigned active = __ballot_sync(FULL, f.y != 0u);
         while (active) {
             const int i = __ffs(active) - 1;
             active &= active - 1;
             const int cl = wid * PER_WARP + i;
-            const unsigned tb = __shfl_sync(FULL, f_lo, i) - tile_base;
-            const CellWords w = load_cell_words(S, g, k0 + cl);
-            const unsigned used = used_mask(w);
-            const unsigned code = bit(used, lane) ? cell_code<DISO_ALG_MC>(w, lane) : 0u;
+            const unsigned tb = __shfl_sync(FULL, f.x, i) - tile_base;
+            const unsigned used = __shfl_sync(FULL, f.y, i);
+            // per-cell word written by classify_scan: case index | offset of the cell's first triangle << 8
+            const unsigned info = bit(used, lane) ? C[(size_t)(k0 + cl) * 32 + lane] : 0u;
+            const unsigned code = info & 0xffu;
             s_code[cl * 32 + lane] = (unsigned char)code;
             const unsigned nt = (unsigned)(s_case[code] >> 60);
-            unsigned incl = nt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                unsigned t = __shfl_up_sync(FULL, incl, d);
-                if (lane >= d) incl += t;
-            }
-            const unsigned slot = tb + incl - nt;
+            const unsigned slot = tb + (info >> 8);
 #pragma unroll
             for (unsigned q = 0; q < 5; ++q)
                 if (q < nt) s_list[slot + q] = (unsigned short)((cl << 8) | (lane << 3) | q);

@@ -6,8 +6,8 @@
 //                         dL/d(edge crossing) = sum over the 4 cells around the edge of
 //                         adj_dual[patch of the edge in that cell] / len(patch).
 // Both visit, per crossing edge, the four cells around it.  A cell's data (possibly complemented
-// case index + id of its first dual vertex) is read from the per-cell array C written once by the
-// dual-vertex kernel, instead of being re-derived from 8 sign words 7 times per grid point.
+// case index + id of its first dual vertex) is read from the per-cell array C written once by
+// classify_scan, instead of being re-derived from 8 sign words 7 times per grid point.
 #pragma once
 #include "compact.cuh"
 #include "tables.cuh"
@@ -91,10 +91,9 @@ constexpr int CT_MAX_PATCHES = CT_CHUNKS * 128;
 // The reference recomputes every edge crossing on the fly in each of the 4 cells around the
 // edge (cudualmc.cu:946-948).  Here the crossings are evaluated ONCE by edge_verts_kernel in
 // the raw padded frame into `mcv` (caller scratch, [n_edges,3]) and this kernel only averages:
-//   phase A  lane == cell: (possibly complemented) case index, patch count and first-dual-
-//            vertex id of every cell of the tile's active chunks -> per-cell array C (global,
-//            consumed by the quad / adjoint kernels) + one descriptor per patch in the shared
-//            list at slot (dual vertex id - first id of the tile).
+//   phase A  lane == cell: the per-cell word written by classify_scan ((possibly complemented)
+//            case index | offset of the cell's first dual vertex) -> one descriptor per patch in
+//            the shared list at slot (dual vertex id - first id of the tile).
 //   phase B  thread == dual vertex: gather the crossings of the patch's member edges by rank in
 //            ascending edge id (== the reference's table order, asserted in
 //            tools/extract_tables.py), sum, scale by 1/len, apply the epilogue, store at
@@ -102,10 +101,9 @@ constexpr int CT_MAX_PATCHES = CT_CHUNKS * 128;
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(CT_THREADS) dmc_dual_verts_kernel(const T *__restrict__ mcv, Geo g, EpilogueC<T> epi,
-                                                                  const unsigned *__restrict__ S,
                                                                   const uint4 *__restrict__ E,
                                                                   const uint4 *__restrict__ P,
-                                                                  unsigned short *__restrict__ C, T *__restrict__ verts)
+                                                                  const unsigned short *__restrict__ C, T *__restrict__ verts)
 {
     __shared__ unsigned short s_list[CT_MAX_PATCHES];
     __shared__ unsigned short s_cell[CT_CHUNKS * 32];
@@ -131,19 +129,19 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_dual_verts_kernel(const T *__r
     constexpr int PER_WARP = CT_CHUNKS / CT_WARPS;
     {
         const int kmine = k0 + wid * PER_WARP + lane;
-        bool act = false;
-        if (lane < PER_WARP && kmine < kend) act = P[kmine + 1].x != P[kmine].x;
-        unsigned active = __ballot_sync(FULL, act);
+        uint4 pr = make_uint4(0, 0, 0, 0);
+        if (lane < PER_WARP && kmine < kend) pr = P[kmine];
+        unsigned active = __ballot_sync(FULL, pr.y != 0u);
         while (active) {
             const int i = __ffs(active) - 1;
             active &= active - 1;
-            const int cl = wid * PER_WARP + i, k = k0 + cl;
-            const CellInfo ci = dmc_cell_info(S, P, g, s_case, k, lane);
-            const unsigned short info = ci.ce ? (unsigned short)(ci.code | ((ci.first - P[k].x) << 8)) : (unsigned short)0;
-            C[(size_t)k * 32 + lane] = info;
-            s_cell[cl * 32 + lane] = info;
-            const unsigned np = (ci.ce >> 24) & 7u;
-            const unsigned slot = ci.first - tile_base;
+            const int cl = wid * PER_WARP + i;
+            const unsigned pb = __shfl_sync(FULL, pr.x, i) - tile_base;
+            const unsigned used = __shfl_sync(FULL, pr.y, i);
+            const unsigned info = bit(used, lane) ? C[(size_t)(k0 + cl) * 32 + lane] : 0u;
+            s_cell[cl * 32 + lane] = (unsigned short)info;
+            const unsigned np = bit(used, lane) ? (s_case[info & 0xffu] >> 24) & 7u : 0u;
+            const unsigned slot = pb + (info >> 8);
 #pragma unroll
             for (unsigned q = 0; q < 4; ++q)
                 if (q < np) s_list[slot + q] = (unsigned short)((cl << 7) | (lane << 2) | q);

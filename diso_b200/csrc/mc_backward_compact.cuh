@@ -20,20 +20,15 @@
 // A block that no crossing edge touches skips 1-4 and only writes zeros.
 #pragma once
 #include "compact.cuh"
-#include "mc.cuh"
 
 namespace diso {
 
-constexpr int BC_X = 8, BC_Y = 8;                    // output rows per block
-constexpr int BC_ROWS = (BC_X + 1) * (BC_Y + 1);     // candidate rows incl. the -x / -y halo
-constexpr int BC_PTS = BC_X * BC_Y * 32;             // output points per block
-constexpr int BC_CAP = (BC_X + 1) * BC_Y * 32 + BC_X * (BC_Y + 1) * 32 + BC_X * BC_Y * 33;  // worst-case list length
 constexpr int BC_THREADS = 256;
 
 __device__ __forceinline__ float rcp_fast(float x) { return __frcp_rn(x); }
 __device__ __forceinline__ double rcp_fast(double x) { return 1.0 / x; }
 
-template <typename T, bool HAS_DEF>
+template <typename T, bool HAS_DEF, int BC_X, int BC_Y>
 __global__ void __launch_bounds__(BC_THREADS) mc_backward_compact_kernel(const T *__restrict__ sdf,
                                                                        const T *__restrict__ deform, Geo g, T iso,
                                                                        T padv, T ix, T iy, T iz,
@@ -42,6 +37,9 @@ __global__ void __launch_bounds__(BC_THREADS) mc_backward_compact_kernel(const T
                                                                        T *__restrict__ adj_sdf,
                                                                        T *__restrict__ adj_deform, int ntx, int nty)
 {
+    constexpr int BC_ROWS = (BC_X + 1) * (BC_Y + 1);     // candidate rows incl. the -x / -y halo
+    constexpr int BC_PTS = BC_X * BC_Y * 32;             // output points per block
+    static_assert(BC_ROWS <= 127 && BC_ROWS <= BC_THREADS, "row index must fit the 7-bit descriptor field");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *s_accd = reinterpret_cast<T *>(smem_raw);                       // [BC_PTS]
     T *s_accf = s_accd + BC_PTS;                                       // [BC_PTS * 3] (HAS_DEF only)
@@ -202,8 +200,10 @@ __global__ void __launch_bounds__(BC_THREADS) mc_backward_compact_kernel(const T
     }
 }
 
-template <typename T, bool HAS_DEF> constexpr size_t bwd_compact_smem()
+template <typename T, bool HAS_DEF, int BC_X, int BC_Y> constexpr size_t bwd_compact_smem()
 {
+    constexpr int BC_ROWS = (BC_X + 1) * (BC_Y + 1), BC_PTS = BC_X * BC_Y * 32;
+    constexpr int BC_CAP = (BC_X + 1) * BC_Y * 32 + BC_X * (BC_Y + 1) * 32 + BC_X * BC_Y * 33;  // worst-case list length
     return (size_t)BC_PTS * (HAS_DEF ? 4 : 1) * sizeof(T) + BC_ROWS * sizeof(uint4) + (3 * BC_ROWS + 1 + BC_ROWS) * 4 +
            (size_t)BC_CAP * 2 + 16;
 }

@@ -68,7 +68,7 @@ size_t diso_b200_state_bytes(int alg, int X, int Y, int Z);
 
 /* Byte offsets of the arrays inside `state`, for hosts that want to
  * read the per-chunk prefix sums (slab sharding, diso_b200/parallel.py):
- * out[0..3] = offsets of S (u32), E (uint4), F (u32, MC) | P (uint4, DMC), C (u16, DMC);
+ * out[0..3] = offsets of S (u32), E (uint4), F (uint2, MC) | P (uint4, DMC), C (u16 per cell);
  * out[4] = NC (chunks per padded row), out[5] = NCH (chunks), out[6] = total bytes,
  * out[7] = chunks per padded x-layer.  Entry NCH of E / F / P holds the grand totals. */
 int diso_b200_state_layout(int alg, int X, int Y, int Z, int64_t *out);
@@ -91,8 +91,7 @@ int diso_b200_mc_emit(const void *sdf, const void *deform, int dtype, int X, int
 /* Phase 2, dual marching cubes (replaces create_dmc_verts / create_quads,
  * cudualmc.cu:907-955, 1027-1056, and diso/__init__.py:110-116).
  * verts: [n_verts,3] dtype; quads: [n_quads,4] int64.
- * scratch: caller-owned, n_quads*3 elements of dtype (edge crossings, each evaluated once).
- * This call also completes `state` with the per-cell array diso_b200_dmc_backward needs. */
+ * scratch: caller-owned, n_quads*3 elements of dtype (edge crossings, each evaluated once). */
 int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
                        double iso, const void *state, int normalize, void *scratch, void *verts,
                        int64_t *quads, void *stream);
