@@ -250,18 +250,36 @@ __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const u
             int r = k / g.NC, c = k - r * g.NC;
             int xp = r / g.PY, yp = r - xp * g.PY;
             unsigned short *crow = reinterpret_cast<unsigned short *>(s_cw + tid * CW_STRIDE);
-            unsigned u = used;
-            while (u) {  // ascending j: nb is the cell's offset inside the chunk
-                int j = __ffs(u) - 1;
-                u &= u - 1;
-                unsigned code = cell_code<ALG>(w, j);
-                if (ALG == DISO_ALG_MC) {
+            if (ALG == DISO_ALG_MC) {
+                unsigned u = used;
+                while (u) {  // ascending j: nb is the cell's offset inside the chunk
+                    const int j = __ffs(u) - 1;
+                    u &= u - 1;
+                    const unsigned code = cell_code<ALG>(w, j);
                     crow[j] = (unsigned short)(code | (nb << 8));
                     nb += s_tab[code];
-                } else {
-                    if (dmc_flip(S, g, s_tab, k, xp, yp, c, j, code)) code ^= 0xffu;
+                }
+            } else {
+                // Three passes keep the warp converged: only ~13 % of the used cells of a random field
+                // are "problematic", but inside one per-cell loop nearly every warp iteration would
+                // have SOME lane on the long neighbour-lookup path.
+                unsigned prob = 0;
+                for (unsigned u = used; u; u &= u - 1) {           // 1: raw case index, who needs the test
+                    const int j = __ffs(u) - 1;
+                    const unsigned code = cell_code<ALG>(w, j);
+                    crow[j] = (unsigned short)code;
+                    prob |= (s_tab[code] >> 31) << j;
+                }
+                for (unsigned u = prob; u; u &= u - 1) {           // 2: ambiguity test (cudualmc.cu:815-839)
+                    const int j = __ffs(u) - 1;
+                    const unsigned code = crow[j];
+                    if (dmc_flip(S, g, s_tab, k, xp, yp, c, j, code)) crow[j] = (unsigned short)(code ^ 0xffu);
+                }
+                for (unsigned u = used; u; u &= u - 1) {           // 3: patch counts + offsets, ascending j
+                    const int j = __ffs(u) - 1;
+                    const unsigned code = crow[j];
                     crow[j] = (unsigned short)(code | (nb << 8));
-                    unsigned np = (s_tab[code] >> 24) & 7u;  // 1..4
+                    const unsigned np = (s_tab[code] >> 24) & 7u;  // 1..4
                     nb += np;
                     lo |= ((np - 1u) & 1u) << j;
                     hi |= ((np - 1u) >> 1) << j;
