@@ -161,6 +161,45 @@ def layer_prefixes(alg, state, shape):
     return e.cpu(), f.cpu()
 
 
+def _run_batch(alg, dtype, grad_mode, grids, deforms, isovalue, normalize):
+    """B shapes, ONE host sync: all count phases are enqueued first, the B count blocks are read
+    back together, then every emit runs (the reference's batch loop, README.md:61-70, pays five
+    syncs per shape)."""
+    L = _lib.load()
+    k = 3 if alg == _lib.ALG_MC else 4
+    deforms = list(deforms) if deforms is not None else [None] * len(grids)
+    if len(deforms) != len(grids):
+        raise DisoB200Error("grids and deforms must have the same length")
+    prepared = []
+    for g, d in zip(grids, deforms):
+        _check_inputs(g, d, dtype)
+        if g.device != grids[0].device:
+            raise DisoB200Error("all grids of a batch must live on the same device")
+        prepared.append((g.contiguous(), d.contiguous() if d is not None else None))
+    if not prepared:
+        return []
+    dev = grids[0].device
+    with torch.cuda.device(dev):
+        states = []
+        with torch.no_grad():
+            for g, _ in prepared:
+                X, Y, Z = g.shape
+                nbytes = L.diso_b200_state_bytes(alg, X, Y, Z)
+                state = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                _lib.check(L.diso_b200_count(alg, g.data_ptr(), _DTYPES[g.dtype], X, Y, Z, float(isovalue),
+                                             state.data_ptr(), nbytes, _stream()))
+                states.append(state)
+            heads = torch.stack([s[: 8 * _lib.COUNT_SLOTS].view(torch.int64) for s in states]).cpu().tolist()  # the one sync
+        out = []
+        for (g, d), state, c in zip(prepared, states, heads):
+            if c[_lib.CNT_EDGES] == 0 or c[_lib.CNT_ANY_GT] == 0:
+                out.append((torch.zeros((0, 3), dtype=dtype, device=dev), torch.zeros((0, k), dtype=torch.int32, device=dev)))
+                continue
+            out.append(_Extract.apply(g, d, alg, float(isovalue), bool(normalize), grad_mode, state,
+                                      c[_lib.CNT_VERTS], c[_lib.CNT_FACES]))
+        return out
+
+
 def _grad_mode(name):
     try:
         return {"reference": _lib.GRAD_REFERENCE, "exact": _lib.GRAD_EXACT}[name]
@@ -184,6 +223,10 @@ class DiffMC(nn.Module):
 
     def forward(self, grid, deform=None, isovalue=0.0, normalize=True):
         return _run(_lib.ALG_MC, self.dtype, _lib.GRAD_REFERENCE, grid, deform, isovalue, normalize)
+
+    def forward_batch(self, grids, deforms=None, isovalue=0.0, normalize=True):
+        """List of (verts, faces), one per shape, with a single host synchronisation for the batch."""
+        return _run_batch(_lib.ALG_MC, self.dtype, _lib.GRAD_REFERENCE, grids, deforms, isovalue, normalize)
 
 
 class DiffDMC(nn.Module):
@@ -213,6 +256,13 @@ class DiffDMC(nn.Module):
             # (the reference's early-out returns the (0,4) int32 tensor even when triangles were asked for)
             return verts, quads
         return verts, split_quads(verts.detach(), quads)
+
+    def forward_batch(self, grids, deforms=None, isovalue=0.0, return_quads=False, normalize=True):
+        """List of (verts, faces), one per shape, with a single host synchronisation for the batch."""
+        res = _run_batch(_lib.ALG_DMC, self.dtype, _grad_mode(self.grad_mode), grids, deforms, isovalue, normalize)
+        if return_quads:
+            return res
+        return [(v, q if q.shape[0] == 0 else split_quads(v.detach(), q)) for v, q in res]
 
 
 def split_quads(verts, quads):
