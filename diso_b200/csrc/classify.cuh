@@ -80,7 +80,6 @@ __global__ void __launch_bounds__(256) sign_pack_f32x4_kernel(const float *__res
     unsigned *aw = sm_words + wid * (NA + 2);
     const int nvec = g.Z >> 2;
     const int nb = (nvec + 127) / 128;  // batches of 4 x 32 float4 per row
-    const long long nitems = (long long)g.NR * nb;
     bool any_gt = false;
 
     auto row_ptr = [&](int row) -> const float4 * {
@@ -88,8 +87,7 @@ __global__ void __launch_bounds__(256) sign_pack_f32x4_kernel(const float *__res
         const bool real = xp >= 1 && xp <= g.X && yp >= 1 && yp <= g.Y;
         return real ? reinterpret_cast<const float4 *>(sdf + ((size_t)(xp - 1) * g.Y + (yp - 1)) * g.Z) : nullptr;
     };
-    auto load_batch = [&](long long item, float4 (&q)[4]) {
-        const int row = (int)(item / nb), b = (int)(item - (long long)row * nb);
+    auto load_batch = [&](int row, int b, float4 (&q)[4]) {
         const float4 *rp = row_ptr(row);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -99,13 +97,15 @@ __global__ void __launch_bounds__(256) sign_pack_f32x4_kernel(const float *__res
         }
     };
 
-    long long item = (long long)blockIdx.x * warps_per_cta + wid;
+    // A warp owns whole rows (row = first, first + nwarps, ...) and walks their batches in order,
+    // because the aligned words of a row are staged in the warp's private shared-memory slice.
+    int row = blockIdx.x * warps_per_cta + wid, b = 0;
     float4 q[4], qn[4];
-    if (item < nitems) load_batch(item, q);
-    while (item < nitems) {
-        const long long next = item + nwarps;
-        if (next < nitems) load_batch(next, qn);
-        const int row = (int)(item / nb), b = (int)(item - (long long)row * nb);
+    if (row < g.NR) load_batch(row, 0, q);
+    while (row < g.NR) {
+        int nrow = row, nbat = b + 1;
+        if (nbat == nb) { nrow = row + nwarps; nbat = 0; }
+        if (nrow < g.NR) load_batch(nrow, nbat, qn);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const unsigned nib = (q[u].x >= iso ? 1u : 0u) | (q[u].y >= iso ? 2u : 0u) | (q[u].z >= iso ? 4u : 0u) | (q[u].w >= iso ? 8u : 0u);
@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(256) sign_pack_f32x4_kernel(const float *__res
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) q[u] = qn[u];
-        item = next;
+        row = nrow;
+        b = nbat;
     }
     if (__any_sync(FULL, any_gt) && lane == 0) counts[DISO_CNT_ANY_GT] = 1;
 }

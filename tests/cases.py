@@ -31,6 +31,9 @@ CASES = {
     "ragged_5x9x70": (lambda: syn.random_sdf((5, 9, 70), "dense", 3), True, 0.0),   # 3 chunks per row, Z%4!=0
     "ragged_31x2x30": (lambda: syn.random_sdf((31, 2, 30), "flexi", 4), True, 0.0),  # PZ == 32 exactly
     "ragged_3x4x62": (lambda: syn.random_sdf((3, 4, 62), "dense", 5), False, 0.0),   # PZ == 64 exactly
+    "longrow_3x4x644": (lambda: syn.random_sdf((3, 4, 644), "dense", 13), True, 0.0),   # > 512 values per row: 2 load batches
+    "longrow_2x3x1100": (lambda: syn.random_sdf((2, 3, 1100), "flexi", 14), False, 0.0),  # 3 batches, NC > 32
+    "longrow_1x2x1101": (lambda: syn.random_sdf((1, 2, 1101), "dense", 15), True, 0.0),  # scalar sign pass, NC > 32
     "tiny_1x1x1": (lambda: torch.full((1, 1, 1), -0.3), True, 0.0),
     "tiny_2x2x2": (lambda: syn.random_sdf(2, "dense", 6), True, 0.0),
     "thin_1x7x33": (lambda: syn.random_sdf((1, 7, 33), "dense", 7), True, 0.0),
