@@ -207,8 +207,8 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        os.environ.pop("NCCL_DEBUG")        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     import torch
     import torch.distributed as dist
     import diso_b200
