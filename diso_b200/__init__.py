@@ -85,6 +85,8 @@ class _Extract(Function):
         ctx.n_edges = n_verts if alg == _lib.ALG_MC else n_faces
         ctx.save_for_backward(grid, deform, state)
         ctx.mark_non_differentiable(faces)
+        # do not let autograd allocate + fill a zero "gradient" for the (multi-GB) int64 faces output
+        ctx.set_materialize_grads(False)
         return verts, faces
 
     @staticmethod
@@ -92,8 +94,9 @@ class _Extract(Function):
         grid, deform, state = ctx.saved_tensors
         L = _lib.load()
         X, Y, Z = grid.shape
-        if adj_verts is None:
-            adj_verts = torch.zeros((0, 3), dtype=grid.dtype, device=grid.device)
+        if adj_verts is None:  # verts did not take part in the loss: all gradients are zero
+            return (torch.zeros_like(grid), torch.zeros_like(deform) if deform is not None else None,
+                    None, None, None, None, None, None, None)
         # the reference requires a contiguous adj_verts and raises otherwise (pybind.cpp:142);
         # expanded gradients (e.g. from verts.sum() with normalize=False) are made contiguous here.
         adj_verts = adj_verts.contiguous()
