@@ -54,11 +54,11 @@ inline Geo make_geo(int X, int Y, int Z)
     return g;
 }
 
-// One descriptor per scan tile (decoupled look-back, see classify.cu).
+// One descriptor per scan tile (decoupled look-back, see classify.cuh).
 struct __align__(32) TileDesc {
     unsigned flag;            // 0 = empty, 1 = aggregate available, 2 = inclusive prefix available
     unsigned pad0;
-    unsigned long long agg;   // three 21-bit tile aggregates packed (a | b<<21 | c<<42)
+    unsigned long long agg;   // the tile's two aggregates packed (a | b << 32)
     unsigned long long incl_a;
     unsigned long long incl_b;
 };

@@ -29,8 +29,9 @@ __device__ __forceinline__ unsigned short edge_desc(int chunk_local, int lane, i
     return (unsigned short)((chunk_local << 7) | (lane << 2) | axis);
 }
 
-// Phase A for edge lists.  Fills s_list[rank - tile_base] and s_pos[chunk_local]; returns the
-// number of edges of the tile (uniform).  Must be called by all CT_THREADS threads.
+// Phase A for edge lists.  Fills s_list[rank - tile_base] and (if s_pos != nullptr) the padded
+// coordinates of every chunk of the tile; returns the number of edges of the tile (uniform).
+// Must be called by all CT_THREADS threads.
 // If S != nullptr, bit 13 of each descriptor tells whether the edge's start point is inside
 // (value >= iso), i.e. whether the crossing is "exiting" in the DMC sense (cudualmc.cu:782-788).
 __device__ __forceinline__ unsigned build_edge_list(const Geo &g, const uint4 *__restrict__ E, int k0,
@@ -48,7 +49,7 @@ __device__ __forceinline__ unsigned build_edge_list(const Geo &g, const uint4 *_
     const int kmine = k0 + wid * PER_WARP + lane;
     if (lane < PER_WARP && kmine < kend) mine = E[kmine];
     unsigned active = __ballot_sync(FULL, (mine.y | mine.z | mine.w) != 0u);
-    if (lane < PER_WARP && kmine < kend) {
+    if (s_pos && lane < PER_WARP && kmine < kend) {
         const int r = kmine / g.NC;
         TilePos tp;
         tp.c = (short)(kmine - r * g.NC);

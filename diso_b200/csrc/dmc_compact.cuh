@@ -24,7 +24,6 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
                                                               long long *__restrict__ quads, T *__restrict__ gedge)
 {
     __shared__ unsigned short s_list[CT_MAX_EDGES];
-    __shared__ TilePos s_pos[CT_CHUNKS];
     __shared__ unsigned s_case[256];
     __shared__ unsigned s_plen[256];
     __shared__ unsigned s_quad[8];
@@ -35,7 +34,7 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
     if (threadIdx.x < 8) s_inv[threadIdx.x] = threadIdx.x ? T(1) / T((int)threadIdx.x) : T(0);
     const int k0 = blockIdx.x * CT_CHUNKS;
     unsigned tile_base;
-    const unsigned n = build_edge_list(g, E, k0, s_list, s_pos, tile_base, S);
+    const unsigned n = build_edge_list(g, E, k0, s_list, nullptr, tile_base, S);
     if (n == 0) return;
     __syncthreads();
     for (unsigned i = threadIdx.x; i < n; i += CT_THREADS) {
