@@ -17,6 +17,8 @@ caller's own shell is already >= iso -- so the mesh is the reference's; coordina
 lattice unit further from the origin and shifted back, hence equal to the reference's to 1 ulp
 rather than bit-for-bit.  Input checks mirror pybind.cpp:5-11,57-60 (CUDA, contiguous, dtype).
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -48,11 +50,11 @@ class _Base:
         with torch.cuda.device(grid.device), torch.no_grad():
             state, counts = _count(self._alg, grid, iso)
             nv, nf = counts[_lib.CNT_VERTS], counts[_lib.CNT_FACES]
-            self._last = (state, nv, nf, float(iso))
+            self._last = (state, nv, nf, _lib.counts_array(counts))
             if counts[_lib.CNT_EDGES] == 0:
                 return (torch.zeros((0, 3), dtype=self._dtype, device=grid.device),
                         torch.zeros((0, k), dtype=torch.int32, device=grid.device))
-            verts, faces = _Extract.apply(grid, deform, self._alg, float(iso), False, _lib.GRAD_REFERENCE, state, nv, nf)
+            verts, faces = _Extract.apply(grid, deform, self._alg, float(iso), False, _lib.GRAD_REFERENCE, state, counts)
         # normalize=False output is (padded-frame position - 1) of OUR frame == the caller's frame
         return verts, faces.to(torch.int32)
 
@@ -65,7 +67,7 @@ class _Base:
             self._check(name, t)
         if self._last is None:
             raise DisoB200Error("backward called before forward")
-        state, nv, nf, iso0 = self._last
+        state, nv, nf, counts_c = self._last
         if nv == 0 or (self._alg == _lib.ALG_DMC and nf == 0):
             return
         L = _lib.load()
@@ -82,6 +84,7 @@ class _Base:
             else:
                 scratch = torch.empty((max(nf, 1), 3), dtype=self._dtype, device=grid.device)
                 _lib.check(L.diso_b200_dmc_backward(grid.data_ptr(), p(deform), dt, X, Y, Z, float(iso), state.data_ptr(),
+                                                    ctypes.cast(counts_c, ctypes.c_void_p),
                                                     adj_verts.data_ptr(), 0, _lib.GRAD_REFERENCE, scratch.data_ptr(),
                                                     g_grid.data_ptr(), p(g_def), st))
             adj_grid.add_(g_grid)          # the reference accumulates into the caller's buffers (atomicAdd)

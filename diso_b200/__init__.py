@@ -7,6 +7,8 @@ Drop-in for the reference package ``diso`` (``from diso_b200 import DiffMC, Diff
 Host code is Python/PyTorch (tensor allocation, autograd plumbing, streams); all computation is
 in hand-written sm_100a CUDA kernels behind the C ABI of ``include/diso_b200.h``.
 """
+import ctypes
+
 import torch
 from torch import nn
 from torch.autograd import Function
@@ -68,14 +70,16 @@ class _Extract(Function):
     keeps batch / activation-checkpoint semantics (nothing lives in the extractor object)."""
 
     @staticmethod
-    def forward(ctx, grid, deform, alg, isovalue, normalize, grad_mode, state, n_verts, n_faces):
+    def forward(ctx, grid, deform, alg, isovalue, normalize, grad_mode, state, counts):
         L = _lib.load()
         X, Y, Z = grid.shape
         k = 3 if alg == _lib.ALG_MC else 4
+        n_verts, n_faces = counts[_lib.CNT_VERTS], counts[_lib.CNT_FACES]
+        ctx.counts = _lib.counts_array(counts)   # host copy of the count block: sizes the emit / backward launches
         verts = torch.empty((n_verts, 3), dtype=grid.dtype, device=grid.device)
         faces = torch.empty((n_faces, k), dtype=torch.int64, device=grid.device)
         args = (grid.data_ptr(), _ptr(deform), _DTYPES[grid.dtype], X, Y, Z, float(isovalue), state.data_ptr(),
-                int(bool(normalize)))
+                ctypes.cast(ctx.counts, ctypes.c_void_p), int(bool(normalize)))
         if alg == _lib.ALG_MC:
             _lib.check(L.diso_b200_mc_emit(*args, verts.data_ptr(), faces.data_ptr(), _stream()))
         else:
@@ -96,7 +100,7 @@ class _Extract(Function):
         X, Y, Z = grid.shape
         if adj_verts is None:  # verts did not take part in the loss: all gradients are zero
             return (torch.zeros_like(grid), torch.zeros_like(deform) if deform is not None else None,
-                    None, None, None, None, None, None, None)
+                    None, None, None, None, None, None)
         # the reference requires a contiguous adj_verts and raises otherwise (pybind.cpp:142);
         # expanded gradients (e.g. from verts.sum() with normalize=False) are made contiguous here.
         adj_verts = adj_verts.contiguous()
@@ -112,11 +116,12 @@ class _Extract(Function):
             else:
                 scratch = torch.empty((max(ctx.n_edges, 1), 3), dtype=grid.dtype, device=grid.device)
                 _lib.check(L.diso_b200_dmc_backward(grid.data_ptr(), _ptr(deform), dt, X, Y, Z, ctx.isovalue,
-                                                    state.data_ptr(), adj_verts.data_ptr(), int(ctx.normalize),
+                                                    state.data_ptr(), ctypes.cast(ctx.counts, ctypes.c_void_p),
+                                                    adj_verts.data_ptr(), int(ctx.normalize),
                                                     ctx.grad_mode, scratch.data_ptr(), adj_grid.data_ptr(),
                                                     _ptr(adj_deform), _stream()))
         del need_grid
-        return adj_grid, adj_deform, None, None, None, None, None, None, None
+        return adj_grid, adj_deform, None, None, None, None, None, None
 
 
 def _run(alg, dtype, grad_mode, grid, deform, isovalue, normalize, want_state=False, slab_mode=False):
@@ -137,7 +142,7 @@ def _run(alg, dtype, grad_mode, grid, deform, isovalue, normalize, want_state=Fa
             return out + (None,) if want_state else out
         if max(n_verts, n_faces) >= 2 ** 32 - 1:
             raise DisoB200Error("mesh too large for one call (%d verts, %d faces): shard the grid" % (n_verts, n_faces))
-        out = _Extract.apply(g, d, alg, float(isovalue), bool(normalize), grad_mode, state, n_verts, n_faces)
+        out = _Extract.apply(g, d, alg, float(isovalue), bool(normalize), grad_mode, state, counts)
         return out + (state,) if want_state else out
 
 
@@ -198,8 +203,7 @@ def _run_batch(alg, dtype, grad_mode, grids, deforms, isovalue, normalize):
             if c[_lib.CNT_EDGES] == 0 or c[_lib.CNT_ANY_GT] == 0:
                 out.append((torch.zeros((0, 3), dtype=dtype, device=dev), torch.zeros((0, k), dtype=torch.int32, device=dev)))
                 continue
-            out.append(_Extract.apply(g, d, alg, float(isovalue), bool(normalize), grad_mode, state,
-                                      c[_lib.CNT_VERTS], c[_lib.CNT_FACES]))
+            out.append(_Extract.apply(g, d, alg, float(isovalue), bool(normalize), grad_mode, state, c))
         return out
 
 

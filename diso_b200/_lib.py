@@ -14,7 +14,12 @@ ALG_MC, ALG_DMC = 0, 1
 F32, F64 = 0, 1
 GRAD_REFERENCE, GRAD_EXACT = 0, 1
 COUNT_SLOTS = 8
-CNT_VERTS, CNT_FACES, CNT_ANY_GT, CNT_EDGES, CNT_USED = 0, 1, 2, 3, 4
+CNT_VERTS, CNT_FACES, CNT_ANY_GT, CNT_EDGES, CNT_USED, CNT_EDGE_TILES, CNT_CELL_TILES = 0, 1, 2, 3, 4, 5, 6
+
+
+def counts_array(counts):
+    """ctypes int64[COUNT_SLOTS] holding the host copy of the count block (passed to emit / backward)."""
+    return (ctypes.c_int64 * COUNT_SLOTS)(*[int(c) for c in counts])
 
 # every symbol include/diso_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _d, _sz, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t, ctypes.c_int64
@@ -24,10 +29,10 @@ SIGNATURES = {
     "diso_b200_state_bytes": (_sz, [_i, _i, _i, _i]),
     "diso_b200_state_layout": (_i, [_i, _i, _i, _i, ctypes.POINTER(ctypes.c_int64)]),
     "diso_b200_count": (_i, [_i, _vp, _i, _i, _i, _i, _d, _vp, _sz, _vp]),
-    "diso_b200_mc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _i, _vp, _vp, _vp]),
-    "diso_b200_dmc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _i, _vp, _vp, _vp, _vp]),
+    "diso_b200_mc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp]),
+    "diso_b200_dmc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "diso_b200_mc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp]),
-    "diso_b200_dmc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "diso_b200_dmc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "diso_b200_quad_split_scratch_bytes": (_sz, [_i64]),
     "diso_b200_quad_split": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp]),
     "diso_b200_debug_cell_codes": (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),

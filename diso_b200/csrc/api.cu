@@ -61,6 +61,8 @@ struct StatePtrs {
     uint4 *E;
     void *aux;
     unsigned short *C;
+    unsigned *tiles;      // [0, NT): edge-active tiles, [NT, 2 NT): face-active tiles
+    int n_emit_tiles;
 };
 
 StatePtrs state_ptrs(void *state, const StateLayout &L)
@@ -74,6 +76,8 @@ StatePtrs state_ptrs(void *state, const StateLayout &L)
     p.E = reinterpret_cast<uint4 *>(b + L.off_erec);
     p.aux = b + L.off_aux;
     p.C = reinterpret_cast<unsigned short *>(b + L.off_cell);
+    p.tiles = reinterpret_cast<unsigned *>(b + L.off_tiles);
+    p.n_emit_tiles = L.n_emit_tiles;
     return p;
 }
 
@@ -88,6 +92,16 @@ template <typename T> EpilogueC<T> make_epilogue_c(const Geo &g, int normalize, 
 }
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// launch geometry of the compacted emit kernels: over the active-tile list when the caller passed the
+// counts it read back, else over every tile (tiles == nullptr makes the kernels use blockIdx directly)
+struct TileGrid { int n; const unsigned *list; };
+inline TileGrid tile_grid(const StatePtrs &p, const Geo &g, const int64_t *counts_host, int which)
+{
+    if (!counts_host) return TileGrid{(g.NCH + CT_CHUNKS - 1) / CT_CHUNKS, nullptr};
+    const long long n = counts_host[which ? DISO_CNT_CELL_TILES : DISO_CNT_EDGE_TILES];
+    return TileGrid{(int)std::min<long long>(std::max<long long>(n, 0), p.n_emit_tiles), p.tiles + (size_t)which * p.n_emit_tiles};
+}
 
 inline int sm_count()
 {
@@ -153,35 +167,35 @@ int count_impl(int alg, const T *sdf, const Geo &g, double iso, const StateLayou
         LAUNCH("sign_pack", st, sign_pack_kernel<T><<<cdiv(g.NR, warps), warps * 32, 0, st>>>(sdf, g, isoT, p.S, p.counts));
     }
     if (alg == DISO_ALG_MC)
-        LAUNCH("classify_scan_mc", st, classify_scan_kernel<DISO_ALG_MC><<<L.n_tiles, SCAN_TILE, 0, st>>>(g, p.S, p.E, p.aux, p.C, p.desc, p.ticket, p.counts));
+        LAUNCH("classify_scan_mc", st, classify_scan_kernel<DISO_ALG_MC><<<L.n_tiles, SCAN_TILE, 0, st>>>(g, p.S, p.E, p.aux, p.C, p.tiles, p.n_emit_tiles, p.desc, p.ticket, p.counts));
     else
-        LAUNCH("classify_scan_dmc", st, classify_scan_kernel<DISO_ALG_DMC><<<L.n_tiles, SCAN_TILE, 0, st>>>(g, p.S, p.E, p.aux, p.C, p.desc, p.ticket, p.counts));
+        LAUNCH("classify_scan_dmc", st, classify_scan_kernel<DISO_ALG_DMC><<<L.n_tiles, SCAN_TILE, 0, st>>>(g, p.S, p.E, p.aux, p.C, p.tiles, p.n_emit_tiles, p.desc, p.ticket, p.counts));
     return DISO_OK;
 }
 
 template <typename T>
-int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, int normalize, T *verts,
-                 long long *tris, cudaStream_t st)
+int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const int64_t *counts_host,
+                 int normalize, T *verts, long long *tris, cudaStream_t st)
 {
-    const int grid = cdiv(g.NCH, CT_CHUNKS);
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     const EpilogueC<T> epi = make_epilogue_c<T>(g, normalize);
-    LAUNCH("mc_emit_verts", st, edge_verts_kernel<T><<<grid, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, verts));
-    LAUNCH("mc_emit_tris", st, mc_tris_kernel<<<grid, CT_THREADS, 0, st>>>(g, p.E, reinterpret_cast<const uint2 *>(p.aux), p.C, tris));
+    const TileGrid te = tile_grid(p, g, counts_host, 0), tc = tile_grid(p, g, counts_host, 1);
+    if (te.n) LAUNCH("mc_emit_verts", st, edge_verts_kernel<T><<<te.n, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, verts));
+    if (tc.n) LAUNCH("mc_emit_tris", st, mc_tris_kernel<<<tc.n, CT_THREADS, 0, st>>>(g, p.E, reinterpret_cast<const uint2 *>(p.aux), p.C, tc.list, tris));
     return DISO_OK;
 }
 
 template <typename T>
-int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, int normalize, T *scratch,
-                  T *verts, long long *quads, cudaStream_t st)
+int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const int64_t *counts_host,
+                  int normalize, T *scratch, T *verts, long long *quads, cudaStream_t st)
 {
-    const int grid = cdiv(g.NCH, CT_CHUNKS);
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
     const EpilogueC<T> raw = make_epilogue_c<T>(g, 0, false), epic = make_epilogue_c<T>(g, normalize);
-    LAUNCH("dmc_edge_crossings", st, edge_verts_kernel<T><<<grid, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, scratch));
-    LAUNCH("dmc_emit_verts", st, dmc_dual_verts_kernel<T><<<grid, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, verts));
-    LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0><<<grid, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, T(1), T(1), T(1), nullptr, quads, nullptr)));
+    const TileGrid te = tile_grid(p, g, counts_host, 0), tc = tile_grid(p, g, counts_host, 1);
+    if (te.n) LAUNCH("dmc_edge_crossings", st, edge_verts_kernel<T><<<te.n, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, scratch));
+    if (tc.n) LAUNCH("dmc_emit_verts", st, dmc_dual_verts_kernel<T><<<tc.n, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, tc.list, verts));
+    if (te.n) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0><<<te.n, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, T(1), T(1), T(1), nullptr, quads, nullptr)));
     return DISO_OK;
 }
 
@@ -217,17 +231,19 @@ int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, co
 }
 
 template <typename T>
-int dmc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const T *adj_verts,
-                      int normalize, int grad_mode, T *scratch, T *adj_sdf, T *adj_deform, cudaStream_t st)
+int dmc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const int64_t *counts_host,
+                      const T *adj_verts, int normalize, int grad_mode, T *scratch, T *adj_sdf, T *adj_deform, cudaStream_t st)
 {
     const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
     const T ix = normalize ? T(1) / (T(g.X) - T(1)) : T(1), iy = normalize ? T(1) / (T(g.Y) - T(1)) : T(1),
             iz = normalize ? T(1) / (T(g.Z) - T(1)) : T(1);
-    const int grid2 = cdiv(g.NCH, CT_CHUNKS);
-    if (grad_mode == DISO_GRAD_EXACT)
-        LAUNCH("dmc_edge_adjoint", st, (dmc_edges2_kernel<T, 1><<<grid2, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, ix, iy, iz, adj_verts, nullptr, scratch)));
-    else
-        LAUNCH("dmc_edge_adjoint", st, (dmc_edges2_kernel<T, 2><<<grid2, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, ix, iy, iz, adj_verts, nullptr, scratch)));
+    const TileGrid te = tile_grid(p, g, counts_host, 0);
+    if (te.n) {
+        if (grad_mode == DISO_GRAD_EXACT)
+            LAUNCH("dmc_edge_adjoint", st, (dmc_edges2_kernel<T, 1><<<te.n, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, ix, iy, iz, adj_verts, nullptr, scratch)));
+        else
+            LAUNCH("dmc_edge_adjoint", st, (dmc_edges2_kernel<T, 2><<<te.n, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, ix, iy, iz, adj_verts, nullptr, scratch)));
+    }
     return mc_backward_impl<T>(sdf, deform, g, iso, p, scratch, 0, adj_sdf, adj_deform, st);
 }
 
@@ -308,7 +324,7 @@ int diso_b200_count(int alg, const void *sdf, int dtype, int X, int Y, int Z, do
 }
 
 int diso_b200_mc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
-                      const void *state, int normalize, void *verts, int64_t *tris, void *stream)
+                      const void *state, const int64_t *counts_host, int normalize, void *verts, int64_t *tris, void *stream)
 {
     int rc = check_dims(DISO_ALG_MC, dtype, X, Y, Z);
     if (rc) return rc;
@@ -317,14 +333,15 @@ int diso_b200_mc_emit(const void *sdf, const void *deform, int dtype, int X, int
     const StatePtrs p = state_ptrs(const_cast<void *>(state), make_layout(DISO_ALG_MC, g));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == DISO_F32)
-        return mc_emit_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, normalize,
+        return mc_emit_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, counts_host, normalize,
                                    static_cast<float *>(verts), reinterpret_cast<long long *>(tris), st);
-    return mc_emit_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, normalize,
+    return mc_emit_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, counts_host, normalize,
                                 static_cast<double *>(verts), reinterpret_cast<long long *>(tris), st);
 }
 
 int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
-                       const void *state, int normalize, void *scratch, void *verts, int64_t *quads, void *stream)
+                       const void *state, const int64_t *counts_host, int normalize, void *scratch, void *verts,
+                       int64_t *quads, void *stream)
 {
     int rc = check_dims(DISO_ALG_DMC, dtype, X, Y, Z);
     if (rc) return rc;
@@ -333,9 +350,9 @@ int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, in
     const StatePtrs p = state_ptrs(const_cast<void *>(state), make_layout(DISO_ALG_DMC, g));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == DISO_F32)
-        return dmc_emit_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, normalize,
+        return dmc_emit_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, counts_host, normalize,
                                     static_cast<float *>(scratch), static_cast<float *>(verts), reinterpret_cast<long long *>(quads), st);
-    return dmc_emit_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, normalize,
+    return dmc_emit_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, counts_host, normalize,
                                  static_cast<double *>(scratch), static_cast<double *>(verts), reinterpret_cast<long long *>(quads), st);
 }
 
@@ -360,8 +377,8 @@ int diso_b200_mc_backward(const void *sdf, const void *deform, int dtype, int X,
 }
 
 int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
-                           const void *state, const void *adj_verts, int normalize, int grad_mode, void *scratch,
-                           void *adj_sdf, void *adj_deform, void *stream)
+                           const void *state, const int64_t *counts_host, const void *adj_verts, int normalize,
+                           int grad_mode, void *scratch, void *adj_sdf, void *adj_deform, void *stream)
 {
     int rc = check_dims(DISO_ALG_DMC, dtype, X, Y, Z);
     if (rc) return rc;
@@ -372,10 +389,10 @@ int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X
     const StatePtrs p = state_ptrs(const_cast<void *>(state), make_layout(DISO_ALG_DMC, g));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == DISO_F32)
-        return dmc_backward_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p,
+        return dmc_backward_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, counts_host,
                                         static_cast<const float *>(adj_verts), normalize, grad_mode, static_cast<float *>(scratch),
                                         static_cast<float *>(adj_sdf), static_cast<float *>(adj_deform), st);
-    return dmc_backward_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p,
+    return dmc_backward_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, counts_host,
                                      static_cast<const double *>(adj_verts), normalize, grad_mode, static_cast<double *>(scratch),
                                      static_cast<double *>(adj_sdf), static_cast<double *>(adj_deform), st);
 }

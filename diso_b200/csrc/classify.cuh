@@ -213,6 +213,7 @@ template <int ALG>
 __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const unsigned *__restrict__ S,
                                                                   uint4 *__restrict__ E, void *__restrict__ aux,
                                                                   unsigned short *__restrict__ C,
+                                                                  unsigned *__restrict__ tiles, int n_emit_tiles,
                                                                   TileDesc *__restrict__ desc,
                                                                   unsigned *__restrict__ ticket,
                                                                   long long *__restrict__ counts)
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const u
     // words keeps the per-thread 2-byte writes of one warp in 32 distinct banks
     constexpr int CW_STRIDE = 17;
     __shared__ unsigned s_cw[SCAN_TILE * CW_STRIDE];
+    __shared__ unsigned s_act[2][SCAN_TILE / 64];  // per 64-chunk emit tile: owns edges / has faces
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 #pragma unroll
@@ -233,6 +235,7 @@ __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const u
     if (ALG == DISO_ALG_MC) s_tab[tid] = (unsigned)(T_MC_CASE[tid] >> 60);
     else                    s_tab[tid] = T_DMC_CASE[tid];
     if (tid == 0) { s_tile = atomicAdd(ticket, 1u); s_used_tot = 0; }
+    if (tid < 2 * (SCAN_TILE / 64)) s_act[tid / (SCAN_TILE / 64)][tid % (SCAN_TILE / 64)] = 0u;
     __syncthreads();
     const int tile = (int)s_tile;
     const int k = tile * SCAN_TILE + tid;
@@ -288,6 +291,10 @@ __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const u
             }
         }
     }
+
+    // active 64-chunk emit tiles (flags merged per pair of warps; appended to the lists below)
+    if (__any_sync(FULL, na != 0u) && lane == 0) s_act[0][wid >> 1] = 1u;
+    if (__any_sync(FULL, nb != 0u) && lane == 0) s_act[1][wid >> 1] = 1u;
 
     // ---- tile-local exclusive scan of the packed pair (a | b<<16) -------------------------
     unsigned v = na | (nb << 16);
@@ -362,11 +369,21 @@ __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const u
     const unsigned long long base_a = s_excl[0] + (excl_local & 0xffffu);
     const unsigned long long base_b = s_excl[1] + (excl_local >> 16);
 
-    // flush the staged per-cell words: 16 words (32 cells) per chunk, coalesced
+    // flush the staged per-cell words: 16 words (32 cells) per chunk, coalesced; emit tiles without
+    // used cells are skipped (their words are never read), so sparse surfaces write almost nothing
     {
         unsigned *cout = reinterpret_cast<unsigned *>(C) + (size_t)tile * SCAN_TILE * 16;
         const int rows = min(SCAN_TILE, g.NCH - tile * SCAN_TILE);
-        for (int i = tid; i < rows * 16; i += SCAN_TILE) cout[i] = s_cw[(i >> 4) * CW_STRIDE + (i & 15)];
+        for (int i = tid; i < rows * 16; i += SCAN_TILE)
+            if (s_act[1][i >> 10]) cout[i] = s_cw[(i >> 4) * CW_STRIDE + (i & 15)];
+    }
+    if (tid < 2 * (SCAN_TILE / 64)) {
+        const int which = tid / (SCAN_TILE / 64), t = tid % (SCAN_TILE / 64);
+        const int et = tile * (SCAN_TILE / 64) + t;
+        if (s_act[which][t] && et < n_emit_tiles) {
+            const unsigned long long slot = atomicAdd((unsigned long long *)&counts[which ? DISO_CNT_CELL_TILES : DISO_CNT_EDGE_TILES], 1ull);
+            tiles[(size_t)which * n_emit_tiles + slot] = (unsigned)et;
+        }
     }
     if (k < g.NCH) {
         E[k] = make_uint4((unsigned)base_a, mx, my, mz);

@@ -74,6 +74,8 @@ struct StateLayout {
     size_t off_erec;     // uint4[NCH + rec_tail]
     size_t off_aux;      // MC: uint2 F[NCH + 8] ; DMC: uint4 P[NCH + rec_tail]
     size_t off_cell;     // u16 C[(NCH + 8) * 32] per-cell {case index | offset of first triangle / dual vertex << 8}
+    size_t off_tiles;    // u32 active-tile lists: [0, NT) tiles owning crossing edges, [NT, 2 NT) tiles with faces
+    int n_emit_tiles;    // NT = ceil(NCH / 64)
     size_t total;
     int n_tiles;
     int sign_tail;
@@ -103,6 +105,10 @@ inline StateLayout make_layout(int alg, const Geo &g)
     o = align_up(o, 256);
     L.off_cell = o;
     o += ((size_t)g.NCH + 8) * 32 * 2;
+    o = align_up(o, 256);
+    L.off_tiles = o;
+    L.n_emit_tiles = (g.NCH + 63) / 64;
+    o += (size_t)L.n_emit_tiles * 2 * 4;
     L.total = align_up(o, 256);
     return L;
 }

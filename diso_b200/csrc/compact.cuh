@@ -113,11 +113,12 @@ template <typename T> struct EpilogueC {
 template <typename T>
 __global__ void __launch_bounds__(CT_THREADS) edge_verts_kernel(const T *__restrict__ sdf, const T *__restrict__ deform,
                                                               Geo g, T iso, T padv, EpilogueC<T> epi,
-                                                              const uint4 *__restrict__ E, T *__restrict__ verts)
+                                                              const uint4 *__restrict__ E,
+                                                              const unsigned *__restrict__ tiles, T *__restrict__ verts)
 {
     __shared__ unsigned short s_list[CT_MAX_EDGES];
     __shared__ TilePos s_pos[CT_CHUNKS];
-    const int k0 = blockIdx.x * CT_CHUNKS;
+    const int k0 = (int)(tiles ? tiles[blockIdx.x] : blockIdx.x) * CT_CHUNKS;  // active-tile list from classify_scan
     unsigned tile_base;
     const unsigned n = build_edge_list(g, E, k0, s_list, s_pos, tile_base);
     if (n == 0) return;
@@ -193,14 +194,15 @@ __device__ __forceinline__ unsigned edge_rank(const uint4 (*s_E)[CT_REC], int cl
 constexpr int CT_MAX_TRIS = CT_CHUNKS * 160;
 
 __global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const uint4 *__restrict__ E, const uint2 *__restrict__ F,
-                                                           const unsigned short *__restrict__ C, long long *__restrict__ tris)
+                                                           const unsigned short *__restrict__ C,
+                                                           const unsigned *__restrict__ tiles, long long *__restrict__ tris)
 {
     __shared__ unsigned long long s_case[256];
     __shared__ uint4 s_E[4][CT_REC];
     __shared__ unsigned short s_list[CT_MAX_TRIS];
     __shared__ unsigned char s_code[CT_CHUNKS * 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int k0 = blockIdx.x * CT_CHUNKS;
+    const int k0 = (int)(tiles ? tiles[blockIdx.x] : blockIdx.x) * CT_CHUNKS;
     const int kend = min(k0 + CT_CHUNKS, g.NCH);
     const unsigned tile_base = F[k0].x;
     const unsigned n = F[kend].x - tile_base;

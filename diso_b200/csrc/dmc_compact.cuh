@@ -19,7 +19,8 @@ namespace diso {
 template <typename T, int MODE>
 __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const unsigned *__restrict__ S,
                                                               const uint4 *__restrict__ E, const uint4 *__restrict__ P,
-                                                              const unsigned short *__restrict__ C, T ix, T iy, T iz,
+                                                              const unsigned short *__restrict__ C,
+                                                              const unsigned *__restrict__ tiles, T ix, T iy, T iz,
                                                               const T *__restrict__ adj_dual,
                                                               long long *__restrict__ quads, T *__restrict__ gedge)
 {
@@ -32,7 +33,7 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
     if (MODE != 0) s_plen[threadIdx.x] = T_DMC_PATCHLEN[threadIdx.x];
     if (threadIdx.x < 6) s_quad[threadIdx.x] = T_DMC_QUAD[threadIdx.x];
     if (threadIdx.x < 8) s_inv[threadIdx.x] = threadIdx.x ? T(1) / T((int)threadIdx.x) : T(0);
-    const int k0 = blockIdx.x * CT_CHUNKS;
+    const int k0 = (int)(tiles ? tiles[blockIdx.x] : blockIdx.x) * CT_CHUNKS;
     unsigned tile_base;
     const unsigned n = build_edge_list(g, E, k0, s_list, nullptr, tile_base, S);
     if (n == 0) return;
@@ -102,7 +103,8 @@ template <typename T>
 __global__ void __launch_bounds__(CT_THREADS) dmc_dual_verts_kernel(const T *__restrict__ mcv, Geo g, EpilogueC<T> epi,
                                                                   const uint4 *__restrict__ E,
                                                                   const uint4 *__restrict__ P,
-                                                                  const unsigned short *__restrict__ C, T *__restrict__ verts)
+                                                                  const unsigned short *__restrict__ C,
+                                                                  const unsigned *__restrict__ tiles, T *__restrict__ verts)
 {
     __shared__ unsigned short s_list[CT_MAX_PATCHES];
     __shared__ unsigned short s_cell[CT_CHUNKS * 32];
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_dual_verts_kernel(const T *__r
     __shared__ uint4 s_E[4][CT_REC];
     __shared__ T s_inv[8];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int k0 = blockIdx.x * CT_CHUNKS;
+    const int k0 = (int)(tiles ? tiles[blockIdx.x] : blockIdx.x) * CT_CHUNKS;
     const int kend = min(k0 + CT_CHUNKS, g.NCH);
     const unsigned tile_base = P[k0].x;
     const unsigned n = P[kend].x - tile_base;

@@ -71,7 +71,28 @@ __global__ void __launch_bounds__(BC_THREADS) mc_backward_compact_kernel(const T
         s_off[BC_ROWS + tid] = dxr >= 1 ? __popc(rec.z) : 0;                         // y-edges: rows with dx >= 0
         s_off[2 * BC_ROWS + tid] = (dxr >= 1 && dyr >= 1) ? __popc(rec.w) + zin : 0;  // z-edges: output rows
     }
-    __syncthreads();
+    bool mine_any = false;
+    if (tid < BC_ROWS) mine_any = (s_off[tid] | s_off[BC_ROWS + tid] | s_off[2 * BC_ROWS + tid]) != 0u;
+    if (!__syncthreads_or(mine_any)) {
+        // no crossing edge touches this block (the common case on smooth surfaces): zeros, straight from registers
+        for (int r = wid; r < BC_X * BC_Y; r += BC_THREADS / 32) {
+            const int ox = r / BC_Y, oy = r - ox * BC_Y;
+            const int xp = xp0 + ox, yp = yp0 + oy;
+            if (xp > g.X || yp > g.Y) continue;
+            const long long rowb = ((long long)(xp - 1) * g.Y + (yp - 1)) * g.Z + (32 * c - 1);
+            const int zp = 32 * c + lane;
+            if (zp >= 1 && zp <= g.Z) st_stream(adj_sdf + rowb + lane, T(0));
+            if (HAS_DEF) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int e = lane + 32 * q;
+                    const int zz = 32 * c + e / 3;
+                    if (zz >= 1 && zz <= g.Z) st_stream(adj_deform + 3 * rowb + e, T(0));
+                }
+            }
+        }
+        return;
+    }
     if (wid == 0) {  // exclusive scan of 3*BC_ROWS counts (8 per lane)
         constexpr int N = 3 * BC_ROWS, PER = (N + 31) / 32;
         unsigned v[PER], sum = 0;

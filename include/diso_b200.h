@@ -55,6 +55,8 @@ extern "C" {
 #define DISO_CNT_ANY_GT 2   /* 1 iff some sdf value > iso  (max <= iso  <=>  0)            */
 #define DISO_CNT_EDGES 3    /* #crossing edges (== MC verts == DMC quads)                  */
 #define DISO_CNT_USED 4     /* #used cells (cells whose 8 corners are not all on one side) */
+#define DISO_CNT_EDGE_TILES 5 /* #64-chunk tiles owning >= 1 crossing edge (emit launches only over those) */
+#define DISO_CNT_CELL_TILES 6 /* #64-chunk tiles with >= 1 triangle / dual vertex */
 
 int diso_b200_abi_version(void);
 
@@ -83,18 +85,21 @@ int diso_b200_count(int alg, const void *sdf, int dtype, int X, int Y, int Z, do
 
 /* Phase 2, marching cubes (replaces create_cell_mc_verts / create_cell_mc_tris,
  * cumc.cu:370-410, 564-612, and the epilogue diso/__init__.py:56-61).
- * verts: [n_verts,3] dtype; tris: [n_tris,3] int64.  deform may be NULL. */
+ * verts: [n_verts,3] dtype; tris: [n_tris,3] int64.  deform may be NULL.
+ * counts_host: HOST pointer to the DISO_COUNT_SLOTS int64 the caller read back after
+ * diso_b200_count (the active-tile counts size the launches; sparse surfaces then cost time
+ * proportional to the surface, not the volume).  NULL = launch over every tile. */
 int diso_b200_mc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
-                      double iso, const void *state, int normalize, void *verts, int64_t *tris,
-                      void *stream);
+                      double iso, const void *state, const int64_t *counts_host, int normalize,
+                      void *verts, int64_t *tris, void *stream);
 
 /* Phase 2, dual marching cubes (replaces create_dmc_verts / create_quads,
  * cudualmc.cu:907-955, 1027-1056, and diso/__init__.py:110-116).
  * verts: [n_verts,3] dtype; quads: [n_quads,4] int64.
  * scratch: caller-owned, n_quads*3 elements of dtype (edge crossings, each evaluated once). */
 int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
-                       double iso, const void *state, int normalize, void *scratch, void *verts,
-                       int64_t *quads, void *stream);
+                       double iso, const void *state, const int64_t *counts_host, int normalize,
+                       void *scratch, void *verts, int64_t *quads, void *stream);
 
 /* Backward, marching cubes (replaces adj_create_cell_mc_verts, cumc.cu:474-512, the dense
  * zero-fills of diso/__init__.py:33,40 and the pad-backward slices).  adj_verts is dL/dverts in
@@ -108,9 +113,9 @@ int diso_b200_mc_backward(const void *sdf, const void *deform, int dtype, int X,
 /* Backward, dual marching cubes (replaces adj_create_dmc_verts, cudualmc.cu:957-1005).
  * scratch: caller-owned, n_quads*3 elements of dtype (per-edge adjoints). */
 int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
-                           double iso, const void *state, const void *adj_verts, int normalize,
-                           int grad_mode, void *scratch, void *adj_sdf, void *adj_deform,
-                           void *stream);
+                           double iso, const void *state, const int64_t *counts_host,
+                           const void *adj_verts, int normalize, int grad_mode, void *scratch,
+                           void *adj_sdf, void *adj_deform, void *stream);
 
 /* Quad -> triangle split of diso/__init__.py:118-147 as three small kernels (no PyTorch
  * temporaries).  verts [n_verts,3] dtype (API frame), quads [n_quads,4] int64, faces
