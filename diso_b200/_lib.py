@@ -14,7 +14,7 @@ ALG_MC, ALG_DMC = 0, 1
 F32, F64 = 0, 1
 GRAD_REFERENCE, GRAD_EXACT = 0, 1
 COUNT_SLOTS = 8
-CNT_VERTS, CNT_FACES, CNT_ANY_GT, CNT_EDGES, CNT_USED, CNT_EDGE_TILES, CNT_CELL_TILES = 0, 1, 2, 3, 4, 5, 6
+CNT_VERTS, CNT_FACES, CNT_ANY_GT, CNT_EDGES, CNT_USED, CNT_EDGE_CHUNKS, CNT_CELL_CHUNKS = 0, 1, 2, 3, 4, 5, 6
 
 
 def counts_array(counts):

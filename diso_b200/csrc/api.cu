@@ -61,8 +61,7 @@ struct StatePtrs {
     uint4 *E;
     void *aux;
     unsigned short *C;
-    unsigned *tiles;      // [0, NT): edge-active tiles, [NT, 2 NT): face-active tiles
-    int n_emit_tiles;
+    unsigned *active;     // [0, NCH): chunks owning crossing edges, [NCH, 2 NCH): chunks with faces (ascending)
 };
 
 StatePtrs state_ptrs(void *state, const StateLayout &L)
@@ -76,8 +75,7 @@ StatePtrs state_ptrs(void *state, const StateLayout &L)
     p.E = reinterpret_cast<uint4 *>(b + L.off_erec);
     p.aux = b + L.off_aux;
     p.C = reinterpret_cast<unsigned short *>(b + L.off_cell);
-    p.tiles = reinterpret_cast<unsigned *>(b + L.off_tiles);
-    p.n_emit_tiles = L.n_emit_tiles;
+    p.active = reinterpret_cast<unsigned *>(b + L.off_active);
     return p;
 }
 
@@ -93,14 +91,14 @@ template <typename T> EpilogueC<T> make_epilogue_c(const Geo &g, int normalize, 
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-// launch geometry of the compacted emit kernels: over the active-tile list when the caller passed the
-// counts it read back, else over every tile (tiles == nullptr makes the kernels use blockIdx directly)
-struct TileGrid { int n; const unsigned *list; };
+// launch geometry of the compacted emit kernels: over the ordered active-chunk list when the caller
+// passed the counts it read back, else over every chunk (list == nullptr: entry i is chunk i)
+struct TileGrid { int ctas; int n_active; const unsigned *list; };
 inline TileGrid tile_grid(const StatePtrs &p, const Geo &g, const int64_t *counts_host, int which)
 {
-    if (!counts_host) return TileGrid{(g.NCH + CT_CHUNKS - 1) / CT_CHUNKS, nullptr};
-    const long long n = counts_host[which ? DISO_CNT_CELL_TILES : DISO_CNT_EDGE_TILES];
-    return TileGrid{(int)std::min<long long>(std::max<long long>(n, 0), p.n_emit_tiles), p.tiles + (size_t)which * p.n_emit_tiles};
+    if (!counts_host) return TileGrid{(g.NCH + CT_CHUNKS - 1) / CT_CHUNKS, g.NCH, nullptr};
+    const int n = (int)std::min<long long>(std::max<long long>(counts_host[which ? DISO_CNT_CELL_CHUNKS : DISO_CNT_EDGE_CHUNKS], 0), g.NCH);
+    return TileGrid{(n + CT_CHUNKS - 1) / CT_CHUNKS, n, p.active + (size_t)which * g.NCH};
 }
 
 inline int sm_count()
@@ -167,9 +165,9 @@ int count_impl(int alg, const T *sdf, const Geo &g, double iso, const StateLayou
         LAUNCH("sign_pack", st, sign_pack_kernel<T><<<cdiv(g.NR, warps), warps * 32, 0, st>>>(sdf, g, isoT, p.S, p.counts));
     }
     if (alg == DISO_ALG_MC)
-        LAUNCH("classify_scan_mc", st, classify_scan_kernel<DISO_ALG_MC><<<L.n_tiles, SCAN_TILE, 0, st>>>(g, p.S, p.E, p.aux, p.C, p.tiles, p.n_emit_tiles, p.desc, p.ticket, p.counts));
+        LAUNCH("classify_scan_mc", st, classify_scan_kernel<DISO_ALG_MC><<<L.n_tiles, SCAN_TILE, 0, st>>>(g, p.S, p.E, p.aux, p.C, p.active, p.desc, p.ticket, p.counts));
     else
-        LAUNCH("classify_scan_dmc", st, classify_scan_kernel<DISO_ALG_DMC><<<L.n_tiles, SCAN_TILE, 0, st>>>(g, p.S, p.E, p.aux, p.C, p.tiles, p.n_emit_tiles, p.desc, p.ticket, p.counts));
+        LAUNCH("classify_scan_dmc", st, classify_scan_kernel<DISO_ALG_DMC><<<L.n_tiles, SCAN_TILE, 0, st>>>(g, p.S, p.E, p.aux, p.C, p.active, p.desc, p.ticket, p.counts));
     return DISO_OK;
 }
 
@@ -180,8 +178,8 @@ int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const 
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     const EpilogueC<T> epi = make_epilogue_c<T>(g, normalize);
     const TileGrid te = tile_grid(p, g, counts_host, 0), tc = tile_grid(p, g, counts_host, 1);
-    if (te.n) LAUNCH("mc_emit_verts", st, edge_verts_kernel<T><<<te.n, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, verts));
-    if (tc.n) LAUNCH("mc_emit_tris", st, mc_tris_kernel<<<tc.n, CT_THREADS, 0, st>>>(g, p.E, reinterpret_cast<const uint2 *>(p.aux), p.C, tc.list, tris));
+    if (te.ctas) LAUNCH("mc_emit_verts", st, edge_verts_kernel<T><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, te.n_active, verts));
+    if (tc.ctas) LAUNCH("mc_emit_tris", st, mc_tris_kernel<<<tc.ctas, CT_THREADS, 0, st>>>(g, p.E, reinterpret_cast<const uint2 *>(p.aux), p.C, tc.list, tc.n_active, tris));
     return DISO_OK;
 }
 
@@ -193,9 +191,9 @@ int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const
     const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
     const EpilogueC<T> raw = make_epilogue_c<T>(g, 0, false), epic = make_epilogue_c<T>(g, normalize);
     const TileGrid te = tile_grid(p, g, counts_host, 0), tc = tile_grid(p, g, counts_host, 1);
-    if (te.n) LAUNCH("dmc_edge_crossings", st, edge_verts_kernel<T><<<te.n, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, scratch));
-    if (tc.n) LAUNCH("dmc_emit_verts", st, dmc_dual_verts_kernel<T><<<tc.n, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, tc.list, verts));
-    if (te.n) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0><<<te.n, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, T(1), T(1), T(1), nullptr, quads, nullptr)));
+    if (te.ctas) LAUNCH("dmc_edge_crossings", st, edge_verts_kernel<T><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch));
+    if (tc.ctas) LAUNCH("dmc_emit_verts", st, dmc_dual_verts_kernel<T><<<tc.ctas, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, tc.list, tc.n_active, verts));
+    if (te.ctas) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, quads, nullptr)));
     return DISO_OK;
 }
 
@@ -238,11 +236,11 @@ int dmc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, c
     const T ix = normalize ? T(1) / (T(g.X) - T(1)) : T(1), iy = normalize ? T(1) / (T(g.Y) - T(1)) : T(1),
             iz = normalize ? T(1) / (T(g.Z) - T(1)) : T(1);
     const TileGrid te = tile_grid(p, g, counts_host, 0);
-    if (te.n) {
+    if (te.ctas) {
         if (grad_mode == DISO_GRAD_EXACT)
-            LAUNCH("dmc_edge_adjoint", st, (dmc_edges2_kernel<T, 1><<<te.n, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, ix, iy, iz, adj_verts, nullptr, scratch)));
+            LAUNCH("dmc_edge_adjoint", st, (dmc_edges2_kernel<T, 1><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, ix, iy, iz, adj_verts, nullptr, scratch)));
         else
-            LAUNCH("dmc_edge_adjoint", st, (dmc_edges2_kernel<T, 2><<<te.n, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, ix, iy, iz, adj_verts, nullptr, scratch)));
+            LAUNCH("dmc_edge_adjoint", st, (dmc_edges2_kernel<T, 2><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, ix, iy, iz, adj_verts, nullptr, scratch)));
     }
     return mc_backward_impl<T>(sdf, deform, g, iso, p, scratch, 0, adj_sdf, adj_deform, st);
 }

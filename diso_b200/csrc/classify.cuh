@@ -213,21 +213,21 @@ template <int ALG>
 __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const unsigned *__restrict__ S,
                                                                   uint4 *__restrict__ E, void *__restrict__ aux,
                                                                   unsigned short *__restrict__ C,
-                                                                  unsigned *__restrict__ tiles, int n_emit_tiles,
+                                                                  unsigned *__restrict__ active,
                                                                   TileDesc *__restrict__ desc,
                                                                   unsigned *__restrict__ ticket,
                                                                   long long *__restrict__ counts)
 {
     __shared__ unsigned s_tab[256];  // MC: triangle count per case; DMC: T_DMC_CASE
     __shared__ unsigned s_tile;
-    __shared__ unsigned s_warp_tot[SCAN_TILE / 32];
-    __shared__ unsigned long long s_excl[2];
+    __shared__ unsigned long long s_warp_tot[SCAN_TILE / 32];
+    __shared__ unsigned long long s_excl[4];
     __shared__ unsigned s_used_tot;
     // per-cell words of the tile, staged so they leave the SM as coalesced stores: row stride of 17
     // words keeps the per-thread 2-byte writes of one warp in 32 distinct banks
     constexpr int CW_STRIDE = 17;
     __shared__ unsigned s_cw[SCAN_TILE * CW_STRIDE];
-    __shared__ unsigned s_act[2][SCAN_TILE / 64];  // per 64-chunk emit tile: owns edges / has faces
+    __shared__ unsigned s_any_cells;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 #pragma unroll
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const u
     if (ALG == DISO_ALG_MC) s_tab[tid] = (unsigned)(T_MC_CASE[tid] >> 60);
     else                    s_tab[tid] = T_DMC_CASE[tid];
     if (tid == 0) { s_tile = atomicAdd(ticket, 1u); s_used_tot = 0; }
-    if (tid < 2 * (SCAN_TILE / 64)) s_act[tid / (SCAN_TILE / 64)][tid % (SCAN_TILE / 64)] = 0u;
+    if (tid == 0) s_any_cells = 0u;
     __syncthreads();
     const int tile = (int)s_tile;
     const int k = tile * SCAN_TILE + tid;
@@ -292,98 +292,101 @@ __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const u
         }
     }
 
-    // active 64-chunk emit tiles (flags merged per pair of warps; appended to the lists below)
-    if (__any_sync(FULL, na != 0u) && lane == 0) s_act[0][wid >> 1] = 1u;
-    if (__any_sync(FULL, nb != 0u) && lane == 0) s_act[1][wid >> 1] = 1u;
+    if (__any_sync(FULL, nused != 0u) && lane == 0) s_any_cells = 1u;
 
-    // ---- tile-local exclusive scan of the packed pair (a | b<<16) -------------------------
-    unsigned v = na | (nb << 16);
-    unsigned inc = v;
+    // ---- tile-local exclusive scan of the packed quadruple (a | b<<16 | c<<32 | d<<48) -------
+    const unsigned long long v = (unsigned long long)na | ((unsigned long long)nb << 16) |
+                                 ((unsigned long long)(na != 0u) << 32) | ((unsigned long long)(nb != 0u) << 48);
+    unsigned long long inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        unsigned t = __shfl_up_sync(FULL, inc, d);
+        unsigned long long t = __shfl_up_sync(FULL, inc, d);
         if (lane >= d) inc += t;
     }
     if (lane == 31) s_warp_tot[wid] = inc;
     unsigned ucnt = __reduce_add_sync(FULL, nused);
     if (lane == 0 && ucnt) atomicAdd(&s_used_tot, ucnt);
     __syncthreads();
-    unsigned warp_off = 0, tile_tot = 0;
+    unsigned long long warp_off = 0, tile_tot = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_TILE / 32; ++i) {
-        unsigned t = s_warp_tot[i];
+        unsigned long long t = s_warp_tot[i];
         if (i < wid) warp_off += t;
         tile_tot += t;
     }
-    const unsigned excl_local = warp_off + inc - v;
+    const unsigned long long excl_local = warp_off + inc - v;
 
     // ---- decoupled look-back across tiles (warp 0) ----------------------------------------
     if (wid == 0) {
-        const unsigned long long agg = (unsigned long long)(tile_tot & 0xffffu) | ((unsigned long long)(tile_tot >> 16) << 32);
-        unsigned long long ea = 0, eb = 0;
+        unsigned long long e[4] = {0, 0, 0, 0};
         if (tile == 0) {
             if (lane == 0) {
-                st_relaxed_u64(&desc[0].incl_a, agg & 0xffffffffull);
-                st_relaxed_u64(&desc[0].incl_b, agg >> 32);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) st_relaxed_u64(&desc[0].incl[q], (tile_tot >> (16 * q)) & 0xffffull);
                 st_release_u32(&desc[0].flag, 2u);
             }
         } else {
             if (lane == 0) {
-                st_relaxed_u64(&desc[tile].agg, agg);
+                st_relaxed_u64(&desc[tile].agg, tile_tot);
                 st_release_u32(&desc[tile].flag, 1u);
             }
             int base = tile - 1;
             while (true) {
                 const int t = base - lane;
                 unsigned f = 2u;
-                unsigned long long a = 0, b = 0;
+                unsigned long long x[4] = {0, 0, 0, 0};
                 if (t >= 0) {
                     do { f = ld_acquire_u32(&desc[t].flag); } while (f == 0u);
-                    if (f == 2u) { a = ld_relaxed_u64(&desc[t].incl_a); b = ld_relaxed_u64(&desc[t].incl_b); }
-                    else { unsigned long long q = ld_relaxed_u64(&desc[t].agg); a = q & 0xffffffffull; b = q >> 32; }
+                    if (f == 2u) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) x[q] = ld_relaxed_u64(&desc[t].incl[q]);
+                    } else {
+                        const unsigned long long pk = ld_relaxed_u64(&desc[t].agg);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) x[q] = (pk >> (16 * q)) & 0xffffull;
+                    }
                 }
                 const unsigned m = __ballot_sync(FULL, f == 2u);
                 const int stop = m ? (__ffs(m) - 1) : 32;  // nearest predecessor with an inclusive prefix
-                if (lane > stop) { a = 0; b = 0; }
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    a += __shfl_xor_sync(FULL, a, d);
-                    b += __shfl_xor_sync(FULL, b, d);
+                for (int q = 0; q < 4; ++q) {
+                    if (lane > stop) x[q] = 0;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) x[q] += __shfl_xor_sync(FULL, x[q], d);
+                    e[q] += x[q];
                 }
-                ea += a; eb += b;
                 if (m) break;
                 base -= 32;
             }
             if (lane == 0) {
-                st_relaxed_u64(&desc[tile].incl_a, ea + (agg & 0xffffffffull));
-                st_relaxed_u64(&desc[tile].incl_b, eb + (agg >> 32));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) st_relaxed_u64(&desc[tile].incl[q], e[q] + ((tile_tot >> (16 * q)) & 0xffffull));
                 st_release_u32(&desc[tile].flag, 2u);
             }
         }
         if (lane == 0) {
-            s_excl[0] = ea; s_excl[1] = eb;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s_excl[q] = e[q];
             if (s_used_tot) atomicAdd((unsigned long long *)&counts[DISO_CNT_USED], (unsigned long long)s_used_tot);
         }
     }
     __syncthreads();
-    const unsigned long long base_a = s_excl[0] + (excl_local & 0xffffu);
-    const unsigned long long base_b = s_excl[1] + (excl_local >> 16);
+    const unsigned long long base_a = s_excl[0] + (excl_local & 0xffffull);
+    const unsigned long long base_b = s_excl[1] + ((excl_local >> 16) & 0xffffull);
+    const unsigned long long base_c = s_excl[2] + ((excl_local >> 32) & 0xffffull);
+    const unsigned long long base_d = s_excl[3] + (excl_local >> 48);
 
-    // flush the staged per-cell words: 16 words (32 cells) per chunk, coalesced; emit tiles without
-    // used cells are skipped (their words are never read), so sparse surfaces write almost nothing
-    {
+    // flush the staged per-cell words: 16 words (32 cells) per chunk, coalesced; a scan tile without
+    // used cells is skipped (its words are never read), so sparse surfaces write almost nothing
+    if (s_any_cells) {
         unsigned *cout = reinterpret_cast<unsigned *>(C) + (size_t)tile * SCAN_TILE * 16;
         const int rows = min(SCAN_TILE, g.NCH - tile * SCAN_TILE);
-        for (int i = tid; i < rows * 16; i += SCAN_TILE)
-            if (s_act[1][i >> 10]) cout[i] = s_cw[(i >> 4) * CW_STRIDE + (i & 15)];
+        for (int i = tid; i < rows * 16; i += SCAN_TILE) cout[i] = s_cw[(i >> 4) * CW_STRIDE + (i & 15)];
     }
-    if (tid < 2 * (SCAN_TILE / 64)) {
-        const int which = tid / (SCAN_TILE / 64), t = tid % (SCAN_TILE / 64);
-        const int et = tile * (SCAN_TILE / 64) + t;
-        if (s_act[which][t] && et < n_emit_tiles) {
-            const unsigned long long slot = atomicAdd((unsigned long long *)&counts[which ? DISO_CNT_CELL_TILES : DISO_CNT_EDGE_TILES], 1ull);
-            tiles[(size_t)which * n_emit_tiles + slot] = (unsigned)et;
-        }
+    // ordered active-chunk lists (ascending chunk id): what the emit kernels iterate over
+    if (k < g.NCH) {
+        if (na) active[base_c] = (unsigned)k;
+        if (nb) active[(size_t)g.NCH + base_d] = (unsigned)k;
     }
     if (k < g.NCH) {
         E[k] = make_uint4((unsigned)base_a, mx, my, mz);
@@ -395,6 +398,8 @@ __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const u
         if (ALG == DISO_ALG_MC) reinterpret_cast<uint2 *>(aux)[k] = make_uint2((unsigned)base_b, 0u);
         else reinterpret_cast<uint4 *>(aux)[k] = make_uint4((unsigned)base_b, 0u, 0u, 0u);
         counts[DISO_CNT_EDGES] = (long long)base_a;
+        counts[DISO_CNT_EDGE_CHUNKS] = (long long)base_c;
+        counts[DISO_CNT_CELL_CHUNKS] = (long long)base_d;
         if (ALG == DISO_ALG_MC) { counts[DISO_CNT_VERTS] = (long long)base_a; counts[DISO_CNT_FACES] = (long long)base_b; }
         else                    { counts[DISO_CNT_VERTS] = (long long)base_b; counts[DISO_CNT_FACES] = (long long)base_a; }
     }

@@ -55,12 +55,14 @@ inline Geo make_geo(int X, int Y, int Z)
 }
 
 // One descriptor per scan tile (decoupled look-back, see classify.cuh).
-struct __align__(32) TileDesc {
+// Four quantities are scanned together: a = crossing edges, b = triangles (MC) / dual vertices (DMC),
+// c = chunks owning >= 1 crossing edge, d = chunks with >= 1 face (the last two give the ordered
+// active-chunk lists the emit kernels iterate over).
+struct __align__(64) TileDesc {
     unsigned flag;            // 0 = empty, 1 = aggregate available, 2 = inclusive prefix available
     unsigned pad0;
-    unsigned long long agg;   // the tile's two aggregates packed (a | b << 32)
-    unsigned long long incl_a;
-    unsigned long long incl_b;
+    unsigned long long agg;   // the tile's four aggregates, 16 bits each (a | b<<16 | c<<32 | d<<48)
+    unsigned long long incl[4];
 };
 
 constexpr int SCAN_TILE = 256;  // chunks per scan tile == threads per classify CTA
@@ -74,8 +76,8 @@ struct StateLayout {
     size_t off_erec;     // uint4[NCH + rec_tail]
     size_t off_aux;      // MC: uint2 F[NCH + 8] ; DMC: uint4 P[NCH + rec_tail]
     size_t off_cell;     // u16 C[(NCH + 8) * 32] per-cell {case index | offset of first triangle / dual vertex << 8}
-    size_t off_tiles;    // u32 active-tile lists: [0, NT) tiles owning crossing edges, [NT, 2 NT) tiles with faces
-    int n_emit_tiles;    // NT = ceil(NCH / 64)
+    size_t off_active;   // u32 active-chunk lists (ascending chunk id): [0, NCH) chunks owning crossing
+                         // edges, [NCH, 2 NCH) chunks with faces
     size_t total;
     int n_tiles;
     int sign_tail;
@@ -106,9 +108,8 @@ inline StateLayout make_layout(int alg, const Geo &g)
     L.off_cell = o;
     o += ((size_t)g.NCH + 8) * 32 * 2;
     o = align_up(o, 256);
-    L.off_tiles = o;
-    L.n_emit_tiles = (g.NCH + 63) / 64;
-    o += (size_t)L.n_emit_tiles * 2 * 4;
+    L.off_active = o;
+    o += (size_t)g.NCH * 2 * 4;
     L.total = align_up(o, 256);
     return L;
 }

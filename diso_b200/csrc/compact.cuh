@@ -2,8 +2,11 @@
 //
 // Only ~18 % of the (grid point, axis) slots of a random-init SDF carry a crossing edge (and
 // far fewer on smooth surfaces), so a lane-per-point kernel idles most of its lanes: the ncu
-// baseline (profiles/r1_base_*.txt) shows every such kernel issue-bound with ~15 of 32 threads
-// active.  Instead each CTA owns CT_CHUNKS consecutive chunks and works in two phases:
+// baseline (profiles/r1_base_summary.md) shows every such kernel issue-bound with ~15 of 32 threads
+// active.  Instead each CTA owns a tile of CT_CHUNKS consecutive entries of the ACTIVE-chunk list
+// that classify_scan builds in ascending chunk order (inactive chunks own nothing, so the items
+// of a tile still occupy one contiguous rank range, and a sparse surface costs time proportional
+// to the surface instead of the volume).  A tile is processed in two phases:
 //   phase A  lane == grid point: decode the chunk's edge record and drop a 16-bit descriptor
 //            {chunk-in-tile, lane, axis} for every crossing edge into a shared list.  Because the
 //            records carry GLOBAL exclusive prefix sums, the list slot of an edge is simply
@@ -29,34 +32,46 @@ __device__ __forceinline__ unsigned short edge_desc(int chunk_local, int lane, i
     return (unsigned short)((chunk_local << 7) | (lane << 2) | axis);
 }
 
+// Chunk ids of this CTA's tile: entries [64 b, 64 b + 64) of the active list (`alist == nullptr`:
+// every chunk).  Returns the number of valid entries; s_k[i] = chunk id.  Contains a barrier.
+__device__ __forceinline__ int load_tile_chunks(const unsigned *__restrict__ alist, int n_active, int *s_k)
+{
+    const int e0 = blockIdx.x * CT_CHUNKS;
+    const int count = min(CT_CHUNKS, n_active - e0);
+    if (threadIdx.x < CT_CHUNKS)
+        s_k[threadIdx.x] = (int)threadIdx.x < count ? (alist ? (int)alist[e0 + threadIdx.x] : e0 + (int)threadIdx.x) : 0;
+    __syncthreads();
+    return count;
+}
+
 // Phase A for edge lists.  Fills s_list[rank - tile_base] and (if s_pos != nullptr) the padded
 // coordinates of every chunk of the tile; returns the number of edges of the tile (uniform).
 // Must be called by all CT_THREADS threads.
 // If S != nullptr, bit 13 of each descriptor tells whether the edge's start point is inside
 // (value >= iso), i.e. whether the crossing is "exiting" in the DMC sense (cudualmc.cu:782-788).
-__device__ __forceinline__ unsigned build_edge_list(const Geo &g, const uint4 *__restrict__ E, int k0,
+__device__ __forceinline__ unsigned build_edge_list(const Geo &g, const uint4 *__restrict__ E, const int *s_k, int count,
                                                     unsigned short *s_list, TilePos *s_pos, unsigned &tile_base,
                                                     const unsigned *__restrict__ S = nullptr)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int kend = min(k0 + CT_CHUNKS, g.NCH);
-    tile_base = E[k0].x;
-    const unsigned n = E[kend].x - tile_base;  // E[NCH] holds the grand total
+    tile_base = E[s_k[0]].x;
+    const unsigned n = E[s_k[count - 1] + 1].x - tile_base;  // E[k+1].base = E[k].base + edges of chunk k
     if (n == 0) return 0;
-    // each warp: chunks k0 + wid*8 .. +7 ; lanes 0..7 fetch the records, then broadcast
+    // each warp: entries wid*8 .. +7 ; lanes 0..7 fetch the records, then broadcast
     constexpr int PER_WARP = CT_CHUNKS / CT_WARPS;
     uint4 mine = make_uint4(0, 0, 0, 0);
-    const int kmine = k0 + wid * PER_WARP + lane;
-    if (lane < PER_WARP && kmine < kend) mine = E[kmine];
+    const int emine = wid * PER_WARP + lane;
+    const int kmine = (lane < PER_WARP && emine < count) ? s_k[emine] : -1;
+    if (kmine >= 0) mine = E[kmine];
     unsigned active = __ballot_sync(FULL, (mine.y | mine.z | mine.w) != 0u);
-    if (s_pos && lane < PER_WARP && kmine < kend) {
+    if (s_pos && kmine >= 0) {
         const int r = kmine / g.NC;
         TilePos tp;
         tp.c = (short)(kmine - r * g.NC);
         tp.xp = (short)(r / g.PY);
         tp.yp = (short)(r - (r / g.PY) * g.PY);
         tp.pad = 0;
-        s_pos[wid * PER_WARP + lane] = tp;
+        s_pos[emine] = tp;
     }
     const unsigned lt = lanemask_lt(lane);
     while (active) {
@@ -67,7 +82,7 @@ __device__ __forceinline__ unsigned build_edge_list(const Geo &g, const uint4 *_
         const int cl = wid * PER_WARP + i;
         unsigned slot = base - tile_base + __popc(mx & lt) + __popc(my & lt) + __popc(mz & lt);
         unsigned short in13 = 0;
-        if (S) in13 = (unsigned short)(bit(S[k0 + cl], lane) << 13);
+        if (S) in13 = (unsigned short)(bit(S[__shfl_sync(FULL, kmine, i)], lane) << 13);
         if (bit(mx, lane)) s_list[slot++] = edge_desc(cl, lane, 0) | in13;
         if (bit(my, lane)) s_list[slot++] = edge_desc(cl, lane, 1) | in13;
         if (bit(mz, lane)) s_list[slot] = edge_desc(cl, lane, 2) | in13;
@@ -114,13 +129,15 @@ template <typename T>
 __global__ void __launch_bounds__(CT_THREADS) edge_verts_kernel(const T *__restrict__ sdf, const T *__restrict__ deform,
                                                               Geo g, T iso, T padv, EpilogueC<T> epi,
                                                               const uint4 *__restrict__ E,
-                                                              const unsigned *__restrict__ tiles, T *__restrict__ verts)
+                                                              const unsigned *__restrict__ alist, int n_active,
+                                                              T *__restrict__ verts)
 {
     __shared__ unsigned short s_list[CT_MAX_EDGES];
     __shared__ TilePos s_pos[CT_CHUNKS];
-    const int k0 = (int)(tiles ? tiles[blockIdx.x] : blockIdx.x) * CT_CHUNKS;  // active-tile list from classify_scan
+    __shared__ int s_k[CT_CHUNKS];
+    const int count = load_tile_chunks(alist, n_active, s_k);
     unsigned tile_base;
-    const unsigned n = build_edge_list(g, E, k0, s_list, s_pos, tile_base);
+    const unsigned n = build_edge_list(g, E, s_k, count, s_list, s_pos, tile_base);
     if (n == 0) return;
     __syncthreads();
     const bool has_def = deform != nullptr;
@@ -151,30 +168,42 @@ __global__ void __launch_bounds__(CT_THREADS) edge_verts_kernel(const T *__restr
 
 // ------------------------------------------------------------------------------------------
 // Edge-record cache: the records of the four rows a cell's 12 edges are owned by
-// (rowset = 2*dx + dy of mcEdgeLocations, cumc.cu:109-122), for the tile's chunks plus the
-// following one (dz = 1 from lane 31).  Filled with coalesced 16-byte loads in phase A so that
+// (rowset = 2*dx + dy of mcEdgeLocations, cumc.cu:109-122), for every chunk of the tile and the
+// chunk following it (dz = 1 from lane 31).  Filled with 16-byte loads in phase A so that
 // phase B turns "edge id -> vertex id" into one LDS.128 + three popcounts -- the reference does
 // an owner-cell lookup, two offset loads and a linear search per index (cumc.cu:589-607).
 // ------------------------------------------------------------------------------------------
-constexpr int CT_REC = CT_CHUNKS + 2;
+// Layout [rowset][CT_CHUNKS + 1].  In a contiguous tile (dense surfaces: chunks k0 .. k0+count-1) the
+// "next chunk" of entry cl is simply entry cl + 1 (one extra record per rowset).  In a scattered tile
+// (sparse surfaces) the next chunk is not in the cache; that lookup (only lane 31 with dz = 1) goes to
+// global memory instead -- keeping the cache at 4 KB matters more for occupancy than the rare load.
+constexpr int CT_RECS = 4 * (CT_CHUNKS + 1);
 
-__device__ __forceinline__ void load_record_cache(const Geo &g, const uint4 *__restrict__ E, int k0, uint4 (*s_E)[CT_REC])
+struct RecCache { const uint4 *s_E; const uint4 *E; const int *s_k; int sX, sY; bool contig; };
+
+__device__ __forceinline__ RecCache load_record_cache(const Geo &g, const uint4 *__restrict__ E, const int *s_k, int count, uint4 *s_E)
 {
-    for (int i = threadIdx.x; i < 4 * (CT_CHUNKS + 1); i += CT_THREADS) {
-        const int rs = i / (CT_CHUNKS + 1), cl = i - rs * (CT_CHUNKS + 1);
-        const int kk = k0 + cl + (rs >> 1) * g.sX + (rs & 1) * g.sY;   // E has a zero-filled tail of sX+sY+8 records
-        s_E[rs][cl] = (k0 + cl <= g.NCH) ? __ldg(E + kk) : make_uint4(0, 0, 0, 0);
+    const bool contig = s_k[count - 1] - s_k[0] == count - 1;
+    const int per = contig ? count + 1 : count;
+    for (int i = threadIdx.x; i < 4 * per; i += CT_THREADS) {
+        const int rs = i / per, cl = i - rs * per;
+        const int kk = (contig ? s_k[0] + cl : s_k[cl]) + (rs >> 1) * g.sX + (rs & 1) * g.sY;   // E has a zero-filled tail
+        s_E[rs * (CT_CHUNKS + 1) + cl] = __ldg(E + kk);
     }
+    return RecCache{s_E, E, s_k, g.sX, g.sY, contig};
 }
 
-// vertex id of local edge e of cell (chunk-in-tile cl, lane j)
-__device__ __forceinline__ unsigned edge_rank(const uint4 (*s_E)[CT_REC], int cl, int j, int e)
+// vertex id of local edge e of cell (tile entry cl, lane j)
+__device__ __forceinline__ unsigned edge_rank(const RecCache &rc, int cl, int j, int e)
 {
     const int ax = (EDGE_AX >> (2 * e)) & 3;
     const int rs = (((EDGE_DX >> e) & 1) << 1) | ((EDGE_DY >> e) & 1);
     int jj = j + ((EDGE_DZ >> e) & 1);
-    if (jj == 32) { cl += 1; jj = 0; }
-    const uint4 rec = s_E[rs][cl];
+    const int nxt = jj >> 5;     // dz = 1 from lane 31: first point of the following chunk
+    jj &= 31;
+    uint4 rec;
+    if (nxt && !rc.contig) rec = __ldg(rc.E + rc.s_k[cl] + 1 + (rs >> 1) * rc.sX + (rs & 1) * rc.sY);
+    else rec = rc.s_E[rs * (CT_CHUNKS + 1) + cl + nxt];
     const unsigned l = lanemask_lt(jj);
     unsigned r = rec.x + __popc(rec.y & l) + __popc(rec.z & l) + __popc(rec.w & l);
     if (ax >= 1) r += bit(rec.y, jj);
@@ -195,36 +224,39 @@ constexpr int CT_MAX_TRIS = CT_CHUNKS * 160;
 
 __global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const uint4 *__restrict__ E, const uint2 *__restrict__ F,
                                                            const unsigned short *__restrict__ C,
-                                                           const unsigned *__restrict__ tiles, long long *__restrict__ tris)
+                                                           const unsigned *__restrict__ alist, int n_active,
+                                                           long long *__restrict__ tris)
 {
     __shared__ unsigned long long s_case[256];
-    __shared__ uint4 s_E[4][CT_REC];
+    __shared__ uint4 s_E[CT_RECS];
     __shared__ unsigned short s_list[CT_MAX_TRIS];
     __shared__ unsigned char s_code[CT_CHUNKS * 32];
+    __shared__ int s_k[CT_CHUNKS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int k0 = (int)(tiles ? tiles[blockIdx.x] : blockIdx.x) * CT_CHUNKS;
-    const int kend = min(k0 + CT_CHUNKS, g.NCH);
-    const unsigned tile_base = F[k0].x;
-    const unsigned n = F[kend].x - tile_base;
+    const int count = load_tile_chunks(alist, n_active, s_k);
+    const unsigned tile_base = F[s_k[0]].x;
+    const unsigned n = F[s_k[count - 1] + 1].x - tile_base;
     if (n == 0) return;
     s_case[threadIdx.x] = T_MC_CASE[threadIdx.x];
-    load_record_cache(g, E, k0, s_E);
+    const RecCache rc = load_record_cache(g, E, s_k, count, s_E);
     __syncthreads();
 
     constexpr int PER_WARP = CT_CHUNKS / CT_WARPS;
     {
-        const int kmine = k0 + wid * PER_WARP + lane;
+        const int emine = wid * PER_WARP + lane;
+        const int kmine = (lane < PER_WARP && emine < count) ? s_k[emine] : -1;
         uint2 f = make_uint2(0, 0);
-        if (lane < PER_WARP && kmine < kend) f = F[kmine];
+        if (kmine >= 0) f = F[kmine];
         unsigned active = __ballot_sync(FULL, f.y != 0u);
         while (active) {
             const int i = __ffs(active) - 1;
             active &= active - 1;
             const int cl = wid * PER_WARP + i;
+            const int k = __shfl_sync(FULL, kmine, i);
             const unsigned tb = __shfl_sync(FULL, f.x, i) - tile_base;
             const unsigned used = __shfl_sync(FULL, f.y, i);
             // per-cell word written by classify_scan: case index | offset of the cell's first triangle << 8
-            const unsigned info = bit(used, lane) ? C[(size_t)(k0 + cl) * 32 + lane] : 0u;
+            const unsigned info = bit(used, lane) ? C[(size_t)k * 32 + lane] : 0u;
             const unsigned code = info & 0xffu;
             s_code[cl * 32 + lane] = (unsigned char)code;
             const unsigned nt = (unsigned)(s_case[code] >> 60);
@@ -241,9 +273,9 @@ __global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const uint4 
         const unsigned q = d & 7u;
         const int j = (d >> 3) & 31, cl = (d >> 8) & 63;
         const unsigned tri = (unsigned)(s_case[s_code[cl * 32 + j]] >> (12 * q)) & 0xfffu;
-        const long long a = edge_rank(s_E, cl, j, tri & 15u);
-        const long long b = edge_rank(s_E, cl, j, (tri >> 4) & 15u);
-        const long long c = edge_rank(s_E, cl, j, tri >> 8);
+        const long long a = edge_rank(rc, cl, j, tri & 15u);
+        const long long b = edge_rank(rc, cl, j, (tri >> 4) & 15u);
+        const long long c = edge_rank(rc, cl, j, tri >> 8);
         long long *dst = tris + (size_t)(tile_base + i) * 3;
         st_stream(dst, a); st_stream(dst + 1, b); st_stream(dst + 2, c);
     }

@@ -20,7 +20,7 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const unsigned *__restrict__ S,
                                                               const uint4 *__restrict__ E, const uint4 *__restrict__ P,
                                                               const unsigned short *__restrict__ C,
-                                                              const unsigned *__restrict__ tiles, T ix, T iy, T iz,
+                                                              const unsigned *__restrict__ alist, int n_active, T ix, T iy, T iz,
                                                               const T *__restrict__ adj_dual,
                                                               long long *__restrict__ quads, T *__restrict__ gedge)
 {
@@ -29,19 +29,20 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
     __shared__ unsigned s_plen[256];
     __shared__ unsigned s_quad[8];
     __shared__ T s_inv[8];
+    __shared__ int s_k[CT_CHUNKS];
     s_case[threadIdx.x] = T_DMC_CASE[threadIdx.x];
     if (MODE != 0) s_plen[threadIdx.x] = T_DMC_PATCHLEN[threadIdx.x];
     if (threadIdx.x < 6) s_quad[threadIdx.x] = T_DMC_QUAD[threadIdx.x];
     if (threadIdx.x < 8) s_inv[threadIdx.x] = threadIdx.x ? T(1) / T((int)threadIdx.x) : T(0);
-    const int k0 = (int)(tiles ? tiles[blockIdx.x] : blockIdx.x) * CT_CHUNKS;
+    const int count = load_tile_chunks(alist, n_active, s_k);
     unsigned tile_base;
-    const unsigned n = build_edge_list(g, E, k0, s_list, nullptr, tile_base, S);
+    const unsigned n = build_edge_list(g, E, s_k, count, s_list, nullptr, tile_base, S);
     if (n == 0) return;
     __syncthreads();
     for (unsigned i = threadIdx.x; i < n; i += CT_THREADS) {
         const unsigned d = s_list[i];
         const int axis = d & 3, j = (d >> 2) & 31, cl = (d >> 7) & 63, inside = (d >> 13) & 1;
-        const int k = k0 + cl;
+        const int k = s_k[cl];
         const unsigned q4 = s_quad[inside * 3 + axis];  // reference dmcQuad[type], type = (exiting ? 3 : 0) + axis
         long long id[4];
         Vec3<T> acc{T(0), T(0), T(0)};
@@ -104,42 +105,45 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_dual_verts_kernel(const T *__r
                                                                   const uint4 *__restrict__ E,
                                                                   const uint4 *__restrict__ P,
                                                                   const unsigned short *__restrict__ C,
-                                                                  const unsigned *__restrict__ tiles, T *__restrict__ verts)
+                                                                  const unsigned *__restrict__ alist, int n_active,
+                                                                  T *__restrict__ verts)
 {
     __shared__ unsigned short s_list[CT_MAX_PATCHES];
     __shared__ unsigned short s_cell[CT_CHUNKS * 32];
     __shared__ unsigned s_case[256];
     __shared__ unsigned s_plen[256];
     __shared__ unsigned long long s_members[256];
-    __shared__ uint4 s_E[4][CT_REC];
+    __shared__ uint4 s_E[CT_RECS];
     __shared__ T s_inv[8];
+    __shared__ int s_k[CT_CHUNKS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int k0 = (int)(tiles ? tiles[blockIdx.x] : blockIdx.x) * CT_CHUNKS;
-    const int kend = min(k0 + CT_CHUNKS, g.NCH);
-    const unsigned tile_base = P[k0].x;
-    const unsigned n = P[kend].x - tile_base;
+    const int count = load_tile_chunks(alist, n_active, s_k);
+    const unsigned tile_base = P[s_k[0]].x;
+    const unsigned n = P[s_k[count - 1] + 1].x - tile_base;
     if (n == 0) return;
     s_case[threadIdx.x] = T_DMC_CASE[threadIdx.x];
     s_plen[threadIdx.x] = T_DMC_PATCHLEN[threadIdx.x];
     s_members[threadIdx.x] = T_DMC_MEMBERS[threadIdx.x];
-    load_record_cache(g, E, k0, s_E);
+    const RecCache rc = load_record_cache(g, E, s_k, count, s_E);
     if (threadIdx.x < 8) s_inv[threadIdx.x] = threadIdx.x ? T(1) / T((int)threadIdx.x) : T(0);
     __syncthreads();
 
     // ---- phase A ---------------------------------------------------------------------------------
     constexpr int PER_WARP = CT_CHUNKS / CT_WARPS;
     {
-        const int kmine = k0 + wid * PER_WARP + lane;
+        const int emine = wid * PER_WARP + lane;
+        const int kmine = (lane < PER_WARP && emine < count) ? s_k[emine] : -1;
         uint4 pr = make_uint4(0, 0, 0, 0);
-        if (lane < PER_WARP && kmine < kend) pr = P[kmine];
+        if (kmine >= 0) pr = P[kmine];
         unsigned active = __ballot_sync(FULL, pr.y != 0u);
         while (active) {
             const int i = __ffs(active) - 1;
             active &= active - 1;
             const int cl = wid * PER_WARP + i;
+            const int k = __shfl_sync(FULL, kmine, i);
             const unsigned pb = __shfl_sync(FULL, pr.x, i) - tile_base;
             const unsigned used = __shfl_sync(FULL, pr.y, i);
-            const unsigned info = bit(used, lane) ? C[(size_t)(k0 + cl) * 32 + lane] : 0u;
+            const unsigned info = bit(used, lane) ? C[(size_t)k * 32 + lane] : 0u;
             s_cell[cl * 32 + lane] = (unsigned short)info;
             const unsigned np = bit(used, lane) ? (s_case[info & 0xffu] >> 24) & 7u : 0u;
             const unsigned slot = pb + (info >> 8);
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_dual_verts_kernel(const T *__r
             if (mm) {
                 const int e = __ffs(mm) - 1;
                 mm &= mm - 1;
-                const unsigned r = edge_rank(s_E, cl, j, e);
+                const unsigned r = edge_rank(rc, cl, j, e);
                 rank[t] = r;
             }
         }

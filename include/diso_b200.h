@@ -55,8 +55,8 @@ extern "C" {
 #define DISO_CNT_ANY_GT 2   /* 1 iff some sdf value > iso  (max <= iso  <=>  0)            */
 #define DISO_CNT_EDGES 3    /* #crossing edges (== MC verts == DMC quads)                  */
 #define DISO_CNT_USED 4     /* #used cells (cells whose 8 corners are not all on one side) */
-#define DISO_CNT_EDGE_TILES 5 /* #64-chunk tiles owning >= 1 crossing edge (emit launches only over those) */
-#define DISO_CNT_CELL_TILES 6 /* #64-chunk tiles with >= 1 triangle / dual vertex */
+#define DISO_CNT_EDGE_CHUNKS 5 /* #32-point chunks owning >= 1 crossing edge (the emit kernels visit only those) */
+#define DISO_CNT_CELL_CHUNKS 6 /* #chunks with >= 1 triangle / dual vertex */
 
 int diso_b200_abi_version(void);
 
@@ -87,8 +87,8 @@ int diso_b200_count(int alg, const void *sdf, int dtype, int X, int Y, int Z, do
  * cumc.cu:370-410, 564-612, and the epilogue diso/__init__.py:56-61).
  * verts: [n_verts,3] dtype; tris: [n_tris,3] int64.  deform may be NULL.
  * counts_host: HOST pointer to the DISO_COUNT_SLOTS int64 the caller read back after
- * diso_b200_count (the active-tile counts size the launches; sparse surfaces then cost time
- * proportional to the surface, not the volume).  NULL = launch over every tile. */
+ * diso_b200_count (the active-chunk counts size the launches; sparse surfaces then cost time
+ * proportional to the surface, not the volume).  NULL = visit every chunk. */
 int diso_b200_mc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
                       double iso, const void *state, const int64_t *counts_host, int normalize,
                       void *verts, int64_t *tris, void *stream);
