@@ -44,16 +44,18 @@ def needs_build():
     return False
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, extra=()):
+    """Compile the library.  `out` / `extra` build an experimental variant beside the product
+    (e.g. out=".../libdiso_b200_x.so", extra=["-DDISO_TUNE"]); select it with $DISO_B200_LIB."""
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out or LIB] + SOURCES
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (r.stdout, r.stderr))
     if verbose:
         sys.stderr.write(r.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdiso_b200.so")
+# $DISO_B200_LIB selects another build of the same library (kernel experiments: A/B variants side by side)
+LIB_PATH = os.environ.get("DISO_B200_LIB") or os.path.join(_HERE, "libdiso_b200.so")
 
 ALG_MC, ALG_DMC = 0, 1
 F32, F64 = 0, 1

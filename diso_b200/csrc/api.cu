@@ -5,7 +5,9 @@
 #include <cstring>
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -92,12 +94,16 @@ template <typename T> EpilogueC<T> make_epilogue_c(const Geo &g, int normalize, 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // launch geometry of the compacted emit kernels: over the ordered active-chunk list when the caller
-// passed the counts it read back, else over every chunk (list == nullptr: entry i is chunk i)
+// passed the counts it read back and the surface is sparse, else over every chunk ("dense" tiles of 64
+// consecutive chunks: no indirection; list == nullptr)
 struct TileGrid { int ctas; int n_active; const unsigned *list; };
 inline TileGrid tile_grid(const StatePtrs &p, const Geo &g, const int64_t *counts_host, int which)
 {
-    if (!counts_host) return TileGrid{(g.NCH + CT_CHUNKS - 1) / CT_CHUNKS, g.NCH, nullptr};
+    const TileGrid dense{(g.NCH + CT_CHUNKS - 1) / CT_CHUNKS, g.NCH, nullptr};
+    if (!counts_host) return dense;
     const int n = (int)std::min<long long>(std::max<long long>(counts_host[which ? DISO_CNT_CELL_CHUNKS : DISO_CNT_EDGE_CHUNKS], 0), g.NCH);
+    if (n == 0) return TileGrid{0, 0, nullptr};
+    if ((long long)n * 4 >= (long long)g.NCH * 3) return dense;   // >= 75 % of the chunks are active
     return TileGrid{(n + CT_CHUNKS - 1) / CT_CHUNKS, n, p.active + (size_t)which * g.NCH};
 }
 
@@ -107,6 +113,30 @@ inline int sm_count()
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
         n = 148;  // B200
     return n;
+}
+
+// ---- per-kernel function attributes, applied once per (device, kernel) ----------------------------
+// Preferred shared-memory carve-out in percent of the 228 KB: it decides how much of the SM's 256 KB is
+// left as L1 for the gathers.  The defaults come from sweeps on B200; DISO_CARVEOUT_<NAME> overrides
+// them for experiments (-1 = leave the driver's choice).
+inline int env_int(const char *name, int dflt)
+{
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+inline void kernel_attrs(const void *fn, const char *env, int carveout_pct, size_t dyn_smem = 0)
+{
+    static std::mutex mu;
+    static std::set<std::pair<int, const void *>> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (!done.insert(std::make_pair(dev, fn)).second) return;
+    if (dyn_smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    const int pct = env_int(env, carveout_pct);
+    if (pct >= 0) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(pct, 100));
+    cudaGetLastError();
 }
 
 // ---- tracing: launch counter + optional per-kernel CUDA-event timing (per host thread) --------
@@ -178,8 +208,17 @@ int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const 
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     const EpilogueC<T> epi = make_epilogue_c<T>(g, normalize);
     const TileGrid te = tile_grid(p, g, counts_host, 0), tc = tile_grid(p, g, counts_host, 1);
-    if (te.ctas) LAUNCH("mc_emit_verts", st, edge_verts_kernel<T><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, te.n_active, verts));
-    if (tc.ctas) LAUNCH("mc_emit_tris", st, mc_tris_kernel<<<tc.ctas, CT_THREADS, 0, st>>>(g, p.E, reinterpret_cast<const uint2 *>(p.aux), p.C, tc.list, tc.n_active, tris));
+    kernel_attrs(reinterpret_cast<const void *>(edge_verts_kernel<T, true>), "DISO_CARVEOUT_EV", -1);
+    kernel_attrs(reinterpret_cast<const void *>(edge_verts_kernel<T, false>), "DISO_CARVEOUT_EV", -1);
+    if (te.ctas) {
+        if (te.list) LAUNCH("mc_emit_verts", st, (edge_verts_kernel<T, true><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, te.n_active, verts)));
+        else LAUNCH("mc_emit_verts", st, (edge_verts_kernel<T, false><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, te.n_active, verts)));
+    }
+    if (tc.ctas) {
+        const uint2 *F = reinterpret_cast<const uint2 *>(p.aux);
+        if (tc.list) LAUNCH("mc_emit_tris", st, mc_tris_kernel<true><<<tc.ctas, CT_THREADS, 0, st>>>(g, p.E, F, p.C, tc.list, tc.n_active, tris));
+        else LAUNCH("mc_emit_tris", st, mc_tris_kernel<false><<<tc.ctas, CT_THREADS, 0, st>>>(g, p.E, F, p.C, tc.list, tc.n_active, tris));
+    }
     return DISO_OK;
 }
 
@@ -191,9 +230,24 @@ int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const
     const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
     const EpilogueC<T> raw = make_epilogue_c<T>(g, 0, false), epic = make_epilogue_c<T>(g, normalize);
     const TileGrid te = tile_grid(p, g, counts_host, 0), tc = tile_grid(p, g, counts_host, 1);
-    if (te.ctas) LAUNCH("dmc_edge_crossings", st, edge_verts_kernel<T><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch));
-    if (tc.ctas) LAUNCH("dmc_emit_verts", st, dmc_dual_verts_kernel<T><<<tc.ctas, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, tc.list, tc.n_active, verts));
-    if (te.ctas) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, quads, nullptr)));
+    kernel_attrs(reinterpret_cast<const void *>(edge_verts_kernel<T, true>), "DISO_CARVEOUT_EV", -1);
+    kernel_attrs(reinterpret_cast<const void *>(edge_verts_kernel<T, false>), "DISO_CARVEOUT_EV", -1);
+    kernel_attrs(reinterpret_cast<const void *>(dmc_dual_verts_kernel<T, true>), "DISO_CARVEOUT_DUAL", -1);
+    kernel_attrs(reinterpret_cast<const void *>(dmc_dual_verts_kernel<T, false>), "DISO_CARVEOUT_DUAL", -1);
+    kernel_attrs(reinterpret_cast<const void *>(dmc_edges2_kernel<T, 0, true>), "DISO_CARVEOUT_QUAD", -1);
+    kernel_attrs(reinterpret_cast<const void *>(dmc_edges2_kernel<T, 0, false>), "DISO_CARVEOUT_QUAD", -1);
+    if (te.ctas) {
+        if (te.list) LAUNCH("dmc_edge_crossings", st, (edge_verts_kernel<T, true><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch)));
+        else LAUNCH("dmc_edge_crossings", st, (edge_verts_kernel<T, false><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch)));
+    }
+    if (tc.ctas) {
+        if (tc.list) LAUNCH("dmc_emit_verts", st, (dmc_dual_verts_kernel<T, true><<<tc.ctas, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, tc.list, tc.n_active, verts)));
+        else LAUNCH("dmc_emit_verts", st, (dmc_dual_verts_kernel<T, false><<<tc.ctas, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, tc.list, tc.n_active, verts)));
+    }
+    if (te.ctas) {
+        if (te.list) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, true><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, quads, nullptr)));
+        else LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, false><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, quads, nullptr)));
+    }
     return DISO_OK;
 }
 
@@ -202,16 +256,16 @@ int launch_bwd_compact(const T *sdf, const T *deform, const Geo &g, T isoT, T pa
                        const T *gsrc, T *adj_sdf, T *adj_deform, cudaStream_t st)
 {
     auto kern = mc_backward_compact_kernel<T, HAS_DEF, BX, BY>;
-    constexpr size_t smem = bwd_compact_smem<T, HAS_DEF, BX, BY>();
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static const int smem_pad = env_int("DISO_BWD_SMEM_PAD", 0);   // experiment knob: caps the CTAs per SM
+    const size_t smem = bwd_compact_smem<T, HAS_DEF, BX, BY>() + (size_t)smem_pad;
+    kernel_attrs(reinterpret_cast<const void *>(kern), "DISO_CARVEOUT_BWD", 58, smem);
     const int ntx = cdiv(g.X, BX), nty = cdiv(g.Y, BY);
-    const long long grid = (long long)ntx * nty * g.NC;
-    LAUNCH("mc_backward", st, kern<<<(unsigned)grid, BC_THREADS, smem, st>>>(sdf, deform, g, isoT, padv, ix, iy, iz, E, gsrc, adj_sdf,
-                                                                           adj_deform, ntx, nty));
+    // 3-D grid (chunk, y tile, x tile): no index divisions in the kernel; shapes whose tile counts exceed
+    // the 65535 limit of grid.y / grid.z fall back to a flat grid decoded with divisions
+    const bool flat = nty > 65535 || ntx > 65535;
+    const dim3 grid = flat ? dim3((unsigned)((long long)ntx * nty * g.NC), 1, 1) : dim3((unsigned)g.NC, (unsigned)nty, (unsigned)ntx);
+    LAUNCH("mc_backward", st, kern<<<grid, BC_THREADS, smem, st>>>(sdf, deform, g, isoT, padv, ix, iy, iz, E, gsrc, adj_sdf,
+                                                                 adj_deform, ntx, nty, flat ? 1 : 0));
     return DISO_OK;
 }
 
@@ -224,6 +278,23 @@ int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, co
     const T ix = normalize ? T(1) / (T(g.X) - T(1)) : T(1), iy = normalize ? T(1) / (T(g.Y) - T(1)) : T(1),
             iz = normalize ? T(1) / (T(g.Z) - T(1)) : T(1);
     // block shape from a sweep on B200 (512^3 rand-flexi): 4x8 1.90 ms, 8x4 1.94, 8x8 2.05, 4x4 2.21
+#ifdef DISO_TUNE
+    if (deform && sizeof(T) == 4) {
+        static const int tile = env_int("DISO_BWD_TILE", 0);
+#define DISO_BT(BX, BY) return launch_bwd_compact<T, true, BX, BY>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, adj_verts, adj_sdf, adj_deform, st)
+        switch (tile) {
+        case 1: DISO_BT(4, 4);
+        case 2: DISO_BT(2, 8);
+        case 3: DISO_BT(8, 4);
+        case 4: DISO_BT(2, 16);
+        case 5: DISO_BT(6, 8);
+        case 6: DISO_BT(3, 8);
+        case 7: DISO_BT(4, 6);
+        default: break;
+        }
+#undef DISO_BT
+    }
+#endif
     if (deform) return launch_bwd_compact<T, true, 4, 8>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, adj_verts, adj_sdf, adj_deform, st);
     return launch_bwd_compact<T, false, 4, 8>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, adj_verts, adj_sdf, adj_deform, st);
 }
@@ -237,10 +308,10 @@ int dmc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, c
             iz = normalize ? T(1) / (T(g.Z) - T(1)) : T(1);
     const TileGrid te = tile_grid(p, g, counts_host, 0);
     if (te.ctas) {
-        if (grad_mode == DISO_GRAD_EXACT)
-            LAUNCH("dmc_edge_adjoint", st, (dmc_edges2_kernel<T, 1><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, ix, iy, iz, adj_verts, nullptr, scratch)));
-        else
-            LAUNCH("dmc_edge_adjoint", st, (dmc_edges2_kernel<T, 2><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, ix, iy, iz, adj_verts, nullptr, scratch)));
+#define DISO_ADJ(MODE, LISTED) { kernel_attrs(reinterpret_cast<const void *>(dmc_edges2_kernel<T, MODE, LISTED>), "DISO_CARVEOUT_ADJ", -1); LAUNCH("dmc_edge_adjoint", st, (dmc_edges2_kernel<T, MODE, LISTED><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, ix, iy, iz, adj_verts, nullptr, scratch))); }
+        if (grad_mode == DISO_GRAD_EXACT) { if (te.list) DISO_ADJ(1, true) else DISO_ADJ(1, false) }
+        else                              { if (te.list) DISO_ADJ(2, true) else DISO_ADJ(2, false) }
+#undef DISO_ADJ
     }
     return mc_backward_impl<T>(sdf, deform, g, iso, p, scratch, 0, adj_sdf, adj_deform, st);
 }

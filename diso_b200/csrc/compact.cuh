@@ -7,10 +7,10 @@
 // that classify_scan builds in ascending chunk order (inactive chunks own nothing, so the items
 // of a tile still occupy one contiguous rank range, and a sparse surface costs time proportional
 // to the surface instead of the volume).  A tile is processed in two phases:
-//   phase A  lane == grid point: decode the chunk's edge record and drop a 16-bit descriptor
-//            {chunk-in-tile, lane, axis} for every crossing edge into a shared list.  Because the
-//            records carry GLOBAL exclusive prefix sums, the list slot of an edge is simply
-//            rank - rank_of_first_edge_of_tile: no scan, and list order == output order.
+//   phase A  thread == one byte (8 points) of a chunk's lane masks: walk the set bits and drop a
+//            16-bit descriptor {chunk-in-tile, lane, axis} for every crossing edge into a shared
+//            list.  Because the records carry GLOBAL exclusive prefix sums, the list slot of an edge
+//            is simply rank - rank_of_first_edge_of_tile: no scan, and list order == output order.
 //   phase B  thread == list entry: fully populated warps evaluate one edge each and write the
 //            result at consecutive output ranks (dense, coalesced stores).
 #pragma once
@@ -21,71 +21,90 @@
 namespace diso {
 
 constexpr int CT_CHUNKS = 64;    // chunks per CTA tile
-constexpr int CT_THREADS = 256;  // threads per CTA
+constexpr int CT_THREADS = 256;  // threads per CTA: four threads per chunk in phase A
 constexpr int CT_WARPS = CT_THREADS / 32;
 constexpr int CT_MAX_EDGES = CT_CHUNKS * 96;
+static_assert(CT_THREADS == 4 * CT_CHUNKS, "phase A maps four threads (one byte of the lane masks each) to a chunk");
 
-struct TilePos { short xp, yp, c, pad; };
-
-__device__ __forceinline__ unsigned short edge_desc(int chunk_local, int lane, int axis)
-{
-    return (unsigned short)((chunk_local << 7) | (lane << 2) | axis);
-}
-
-// Chunk ids of this CTA's tile: entries [64 b, 64 b + 64) of the active list (`alist == nullptr`:
-// every chunk).  Returns the number of valid entries; s_k[i] = chunk id.  Contains a barrier.
-__device__ __forceinline__ int load_tile_chunks(const unsigned *__restrict__ alist, int n_active, int *s_k)
-{
-    const int e0 = blockIdx.x * CT_CHUNKS;
-    const int count = min(CT_CHUNKS, n_active - e0);
-    if (threadIdx.x < CT_CHUNKS)
-        s_k[threadIdx.x] = (int)threadIdx.x < count ? (alist ? (int)alist[e0 + threadIdx.x] : e0 + (int)threadIdx.x) : 0;
-    __syncthreads();
-    return count;
-}
-
-// Phase A for edge lists.  Fills s_list[rank - tile_base] and (if s_pos != nullptr) the padded
-// coordinates of every chunk of the tile; returns the number of edges of the tile (uniform).
-// Must be called by all CT_THREADS threads.
-// If S != nullptr, bit 13 of each descriptor tells whether the edge's start point is inside
-// (value >= iso), i.e. whether the crossing is "exiting" in the DMC sense (cudualmc.cu:782-788).
-__device__ __forceinline__ unsigned build_edge_list(const Geo &g, const uint4 *__restrict__ E, const int *s_k, int count,
-                                                    unsigned short *s_list, TilePos *s_pos, unsigned &tile_base,
-                                                    const unsigned *__restrict__ S = nullptr)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    tile_base = E[s_k[0]].x;
-    const unsigned n = E[s_k[count - 1] + 1].x - tile_base;  // E[k+1].base = E[k].base + edges of chunk k
-    if (n == 0) return 0;
-    // each warp: entries wid*8 .. +7 ; lanes 0..7 fetch the records, then broadcast
-    constexpr int PER_WARP = CT_CHUNKS / CT_WARPS;
-    uint4 mine = make_uint4(0, 0, 0, 0);
-    const int emine = wid * PER_WARP + lane;
-    const int kmine = (lane < PER_WARP && emine < count) ? s_k[emine] : -1;
-    if (kmine >= 0) mine = E[kmine];
-    unsigned active = __ballot_sync(FULL, (mine.y | mine.z | mine.w) != 0u);
-    if (s_pos && kmine >= 0) {
-        const int r = kmine / g.NC;
-        TilePos tp;
-        tp.c = (short)(kmine - r * g.NC);
-        tp.xp = (short)(r / g.PY);
-        tp.yp = (short)(r - (r / g.PY) * g.PY);
-        tp.pad = 0;
-        s_pos[emine] = tp;
+// Tiles come in two flavours, selected on the host from the active-chunk counts:
+//   LISTED = false  "dense":  tile b = chunks [64 b, 64 b + 64); no indirection, the +1 neighbour of entry
+//                             cl is entry cl + 1.  Used when most chunks are active (random fields).
+//   LISTED = true   "sparse": tile b = entries [64 b, 64 b + 64) of the ordered active-chunk list.
+template <bool LISTED> struct TileRange {
+    int e0, count, kfirst, klast;
+    const unsigned *alist;
+    __device__ __forceinline__ TileRange(const unsigned *__restrict__ al, int n_active) : alist(al)
+    {
+        e0 = blockIdx.x * CT_CHUNKS;
+        count = min(CT_CHUNKS, n_active - e0);
+        kfirst = LISTED ? (int)__ldg(al + e0) : e0;
+        klast = LISTED ? (int)__ldg(al + e0 + count - 1) : e0 + count - 1;
     }
-    const unsigned lt = lanemask_lt(lane);
-    while (active) {
-        const int i = __ffs(active) - 1;
-        active &= active - 1;
-        const unsigned base = __shfl_sync(FULL, mine.x, i), mx = __shfl_sync(FULL, mine.y, i);
-        const unsigned my = __shfl_sync(FULL, mine.z, i), mz = __shfl_sync(FULL, mine.w, i);
-        const int cl = wid * PER_WARP + i;
-        unsigned slot = base - tile_base + __popc(mx & lt) + __popc(my & lt) + __popc(mz & lt);
-        unsigned short in13 = 0;
-        if (S) in13 = (unsigned short)(bit(S[__shfl_sync(FULL, kmine, i)], lane) << 13);
-        if (bit(mx, lane)) s_list[slot++] = edge_desc(cl, lane, 0) | in13;
-        if (bit(my, lane)) s_list[slot++] = edge_desc(cl, lane, 1) | in13;
-        if (bit(mz, lane)) s_list[slot] = edge_desc(cl, lane, 2) | in13;
+    __device__ __forceinline__ int chunk(int cl) const { return LISTED ? (int)__ldg(alist + e0 + cl) : e0 + cl; }
+};
+
+// Position of a chunk for the value fetches of phase B: 32-bit index of the element "lane 0" of the
+// chunk in the UNPADDED arrays (may lie outside: validity comes from the flags and the z range).
+struct TilePos {
+    int rowbase;     // ((xp-1) Y + (yp-1)) Z + 32 c - 1
+    short xp, yp;
+    int z0;          // 32 c
+    unsigned flags;  // bit0: 1 <= xp <= X   bit1: 1 <= yp <= Y   bit2: xp + 1 <= X   bit3: yp + 1 <= Y
+};
+
+__device__ __forceinline__ TilePos make_tile_pos(const Geo &g, int k)
+{
+    const int r = k / g.NC, c = k - r * g.NC;
+    const int xp = r / g.PY, yp = r - xp * g.PY;
+    TilePos tp;
+    tp.rowbase = ((xp - 1) * g.Y + (yp - 1)) * g.Z + 32 * c - 1;
+    tp.xp = (short)xp; tp.yp = (short)yp;
+    tp.z0 = 32 * c;
+    tp.flags = (unsigned)(xp >= 1 && xp <= g.X) | ((unsigned)(yp >= 1 && yp <= g.Y) << 1) |
+               ((unsigned)(xp + 1 <= g.X) << 2) | ((unsigned)(yp + 1 <= g.Y) << 3);
+    return tp;
+}
+
+// Phase A for edge lists: thread t owns byte (t & 3) of the three crossing masks of tile entry t >> 2
+// and walks its set bits serially (a few per thread), so list building costs ~15 warp instructions
+// per chunk instead of the ~55 of a lane-per-point formulation (ncu, profiles/r1_final_summary.md).
+// Fills s_list[rank - tile_base], s_pos / s_k (when given); returns the number of edges of the tile
+// (uniform).  Must be called by all CT_THREADS threads; the caller synchronises afterwards.
+// SIGN: bit 13 of each descriptor tells whether the edge's start point is inside (value >= iso), i.e.
+// whether the crossing is "exiting" in the DMC sense (cudualmc.cu:782-788).
+template <bool LISTED, bool SIGN>
+__device__ __forceinline__ unsigned build_edge_list(const Geo &g, const uint4 *__restrict__ E, const TileRange<LISTED> &tr,
+                                                    const unsigned *__restrict__ S, unsigned short *s_list, TilePos *s_pos,
+                                                    int *s_k, unsigned &tile_base)
+{
+    tile_base = E[tr.kfirst].x;
+    const unsigned n = E[tr.klast + 1].x - tile_base;  // E[k+1].base = E[k].base + edges of chunk k
+    if (n == 0) return 0;
+    const int cl = threadIdx.x >> 2, sh = (threadIdx.x & 3) * 8;
+    if (cl < tr.count) {
+        const int k = tr.chunk(cl);
+        const uint4 rec = __ldg(E + k);
+        if (sh == 0) {
+            if (LISTED && s_k) s_k[cl] = k;
+            if (s_pos) s_pos[cl] = make_tile_pos(g, k);
+        }
+        const unsigned bx = (rec.y >> sh) & 0xffu, by = (rec.z >> sh) & 0xffu, bz = (rec.w >> sh) & 0xffu;
+        unsigned m = bx | by | bz;
+        if (m) {
+            const unsigned lt = (1u << sh) - 1u;
+            unsigned slot = rec.x - tile_base + __popc(rec.y & lt) + __popc(rec.z & lt) + __popc(rec.w & lt);
+            const unsigned sb = SIGN ? (__ldg(S + k) >> sh) & 0xffu : 0u;
+            const unsigned dbase = ((unsigned)cl << 7) | ((unsigned)sh << 2);
+            do {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                unsigned d = dbase | ((unsigned)j << 2);
+                if (SIGN) d |= ((sb >> j) & 1u) << 13;
+                if ((bx >> j) & 1u) s_list[slot++] = (unsigned short)d;
+                if ((by >> j) & 1u) s_list[slot++] = (unsigned short)(d | 1u);
+                if ((bz >> j) & 1u) s_list[slot++] = (unsigned short)(d | 2u);
+            } while (m);
+        }
     }
     return n;
 }
@@ -125,7 +144,7 @@ template <typename T> struct EpilogueC {
 // epi.normalize == 0 it produces the raw padded-frame crossings that the DMC dual-vertex
 // kernel averages (computeMcVert of cudualmc.cu:683-708, each edge evaluated once, not 4x).
 // ------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool LISTED>
 __global__ void __launch_bounds__(CT_THREADS) edge_verts_kernel(const T *__restrict__ sdf, const T *__restrict__ deform,
                                                               Geo g, T iso, T padv, EpilogueC<T> epi,
                                                               const uint4 *__restrict__ E,
@@ -134,27 +153,38 @@ __global__ void __launch_bounds__(CT_THREADS) edge_verts_kernel(const T *__restr
 {
     __shared__ unsigned short s_list[CT_MAX_EDGES];
     __shared__ TilePos s_pos[CT_CHUNKS];
-    __shared__ int s_k[CT_CHUNKS];
-    const int count = load_tile_chunks(alist, n_active, s_k);
+    const TileRange<LISTED> tr(alist, n_active);
     unsigned tile_base;
-    const unsigned n = build_edge_list(g, E, s_k, count, s_list, s_pos, tile_base);
+    const unsigned n = build_edge_list<LISTED, false>(g, E, tr, nullptr, s_list, s_pos, nullptr, tile_base);
     if (n == 0) return;
     __syncthreads();
     const bool has_def = deform != nullptr;
+    const int sZ = g.Z, sYZ = g.Y * g.Z;
     for (unsigned i = threadIdx.x; i < n; i += CT_THREADS) {
         const unsigned d = s_list[i];
         const int axis = d & 3, j = (d >> 2) & 31;
         const TilePos tp = s_pos[(d >> 7) & 63];
-        const int xp = tp.xp, yp = tp.yp, zp = 32 * tp.c + j;
-        const int xq = xp + (axis == 0), yq = yp + (axis == 1), zq = zp + (axis == 2);
-        const T d0 = fetch_padded(sdf, g, xp, yp, zp, padv);
-        const T d1 = fetch_padded(sdf, g, xq, yq, zq, padv);
+        const int zp = tp.z0 + j, zq = zp + (axis == 2);
+        const unsigned need1 = axis == 0 ? 6u : (axis == 1 ? 9u : 3u);
+        const bool v0 = (tp.flags & 3u) == 3u && (unsigned)(zp - 1) < (unsigned)g.Z;
+        const bool v1 = (tp.flags & need1) == need1 && (unsigned)(zq - 1) < (unsigned)g.Z;
+        const int i0 = tp.rowbase + j;
+        const int i1 = i0 + (axis == 0 ? sYZ : (axis == 1 ? sZ : 1));
+        const T d0 = v0 ? __ldg(sdf + i0) : padv;
+        const T d1 = v1 ? __ldg(sdf + i1) : padv;
         const T t = edge_t(d0, d1, iso);
-        Vec3<T> p0{T(xp), T(yp), T(zp)}, p1{T(xq), T(yq), T(zq)};
+        Vec3<T> p0{T((int)tp.xp), T((int)tp.yp), T(zp)};
+        Vec3<T> p1{T((int)tp.xp + (axis == 0)), T((int)tp.yp + (axis == 1)), T(zq)};
         if (has_def) {
-            const Vec3<T> f0 = fetch_deform(deform, g, xp, yp, zp), f1 = fetch_deform(deform, g, xq, yq, zq);
-            p0.x = p0.x + f0.x; p0.y = p0.y + f0.y; p0.z = p0.z + f0.z;
-            p1.x = p1.x + f1.x; p1.y = p1.y + f1.y; p1.z = p1.z + f1.z;
+            // the pad layer carries zero deformation (diso/__init__.py:54)
+            if (v0) {
+                const T *f = deform + (size_t)i0 * 3;
+                p0.x = p0.x + __ldg(f); p0.y = p0.y + __ldg(f + 1); p0.z = p0.z + __ldg(f + 2);
+            }
+            if (v1) {
+                const T *f = deform + (size_t)i1 * 3;
+                p1.x = p1.x + __ldg(f); p1.y = p1.y + __ldg(f + 1); p1.z = p1.z + __ldg(f + 2);
+            }
         }
         Vec3<T> p;
         p.x = fma_rn(p1.x - p0.x, t, p0.x);
@@ -179,22 +209,26 @@ __global__ void __launch_bounds__(CT_THREADS) edge_verts_kernel(const T *__restr
 // global memory instead -- keeping the cache at 4 KB matters more for occupancy than the rare load.
 constexpr int CT_RECS = 4 * (CT_CHUNKS + 1);
 
-struct RecCache { const uint4 *s_E; const uint4 *E; const int *s_k; int sX, sY; bool contig; };
+template <bool LISTED> struct RecCache { const uint4 *s_E; const uint4 *E; const int *s_k; int sX, sY; bool contig; };
 
-__device__ __forceinline__ RecCache load_record_cache(const Geo &g, const uint4 *__restrict__ E, const int *s_k, int count, uint4 *s_E)
+// s_k (LISTED only) must already hold the tile's chunk ids.
+template <bool LISTED>
+__device__ __forceinline__ RecCache<LISTED> load_record_cache(const Geo &g, const uint4 *__restrict__ E, const TileRange<LISTED> &tr,
+                                                              const int *s_k, uint4 *s_E)
 {
-    const bool contig = s_k[count - 1] - s_k[0] == count - 1;
-    const int per = contig ? count + 1 : count;
+    const bool contig = !LISTED || (tr.klast - tr.kfirst == tr.count - 1);
+    const int per = contig ? tr.count + 1 : tr.count;
     for (int i = threadIdx.x; i < 4 * per; i += CT_THREADS) {
         const int rs = i / per, cl = i - rs * per;
-        const int kk = (contig ? s_k[0] + cl : s_k[cl]) + (rs >> 1) * g.sX + (rs & 1) * g.sY;   // E has a zero-filled tail
+        const int kk = (contig ? tr.kfirst + cl : s_k[cl]) + (rs >> 1) * g.sX + (rs & 1) * g.sY;   // E has a zero-filled tail
         s_E[rs * (CT_CHUNKS + 1) + cl] = __ldg(E + kk);
     }
-    return RecCache{s_E, E, s_k, g.sX, g.sY, contig};
+    return RecCache<LISTED>{s_E, E, s_k, g.sX, g.sY, contig};
 }
 
 // vertex id of local edge e of cell (tile entry cl, lane j)
-__device__ __forceinline__ unsigned edge_rank(const RecCache &rc, int cl, int j, int e)
+template <bool LISTED>
+__device__ __forceinline__ unsigned edge_rank(const RecCache<LISTED> &rc, int cl, int j, int e)
 {
     const int ax = (EDGE_AX >> (2 * e)) & 3;
     const int rs = (((EDGE_DX >> e) & 1) << 1) | ((EDGE_DY >> e) & 1);
@@ -202,7 +236,7 @@ __device__ __forceinline__ unsigned edge_rank(const RecCache &rc, int cl, int j,
     const int nxt = jj >> 5;     // dz = 1 from lane 31: first point of the following chunk
     jj &= 31;
     uint4 rec;
-    if (nxt && !rc.contig) rec = __ldg(rc.E + rc.s_k[cl] + 1 + (rs >> 1) * rc.sX + (rs & 1) * rc.sY);
+    if (LISTED && nxt && !rc.contig) rec = __ldg(rc.E + rc.s_k[cl] + 1 + (rs >> 1) * rc.sX + (rs & 1) * rc.sY);
     else rec = rc.s_E[rs * (CT_CHUNKS + 1) + cl + nxt];
     const unsigned l = lanemask_lt(jj);
     unsigned r = rec.x + __popc(rec.y & l) + __popc(rec.z & l) + __popc(rec.w & l);
@@ -212,16 +246,17 @@ __device__ __forceinline__ unsigned edge_rank(const RecCache &rc, int cl, int j,
 }
 
 // ------------------------------------------------------------------------------------------
-// K4 (v2): triangles, triangle-parallel.  Replaces count_cell_mc_tris / create_cell_mc_tris
+// K4 (v3): triangles, triangle-parallel.  Replaces count_cell_mc_tris / create_cell_mc_tris
 // (cumc.cu:540-612) + the int64 widening (diso/__init__.py:61).
-//   phase A  lane == cell: the per-cell word written by classify_scan (case index | offset of the
-//            cell's first triangle) -> one descriptor {chunk-in-tile, lane, k-th triangle} per
-//            triangle at slot (triangle id - first triangle id of the tile).
+//   phase A  thread == 8 cells of a chunk: the per-cell words written by classify_scan (case index |
+//            offset of the cell's first triangle), fetched as one 128-bit load -> one descriptor
+//            {chunk-in-tile, lane, k-th triangle} per triangle at slot (triangle id - first id of tile).
 //   phase B  thread == triangle: three edge ids from the case table -> three vertex ids via the
 //            record cache -> 24 contiguous bytes at the triangle's output rank.
 // ------------------------------------------------------------------------------------------
 constexpr int CT_MAX_TRIS = CT_CHUNKS * 160;
 
+template <bool LISTED>
 __global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const uint4 *__restrict__ E, const uint2 *__restrict__ F,
                                                            const unsigned short *__restrict__ C,
                                                            const unsigned *__restrict__ alist, int n_active,
@@ -230,40 +265,47 @@ __global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const uint4 
     __shared__ unsigned long long s_case[256];
     __shared__ uint4 s_E[CT_RECS];
     __shared__ unsigned short s_list[CT_MAX_TRIS];
-    __shared__ unsigned char s_code[CT_CHUNKS * 32];
-    __shared__ int s_k[CT_CHUNKS];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int count = load_tile_chunks(alist, n_active, s_k);
-    const unsigned tile_base = F[s_k[0]].x;
-    const unsigned n = F[s_k[count - 1] + 1].x - tile_base;
+    __shared__ __align__(8) unsigned char s_code[CT_CHUNKS * 32];
+    __shared__ int s_k[LISTED ? CT_CHUNKS : 1];
+    const TileRange<LISTED> tr(alist, n_active);
+    const unsigned tile_base = F[tr.kfirst].x;
+    const unsigned n = F[tr.klast + 1].x - tile_base;
     if (n == 0) return;
     s_case[threadIdx.x] = T_MC_CASE[threadIdx.x];
-    const RecCache rc = load_record_cache(g, E, s_k, count, s_E);
+    if (LISTED) {
+        if ((int)threadIdx.x < tr.count) s_k[threadIdx.x] = tr.chunk(threadIdx.x);
+    }
     __syncthreads();
-
-    constexpr int PER_WARP = CT_CHUNKS / CT_WARPS;
+    const RecCache<LISTED> rc = load_record_cache<LISTED>(g, E, tr, s_k, s_E);
     {
-        const int emine = wid * PER_WARP + lane;
-        const int kmine = (lane < PER_WARP && emine < count) ? s_k[emine] : -1;
-        uint2 f = make_uint2(0, 0);
-        if (kmine >= 0) f = F[kmine];
-        unsigned active = __ballot_sync(FULL, f.y != 0u);
-        while (active) {
-            const int i = __ffs(active) - 1;
-            active &= active - 1;
-            const int cl = wid * PER_WARP + i;
-            const int k = __shfl_sync(FULL, kmine, i);
-            const unsigned tb = __shfl_sync(FULL, f.x, i) - tile_base;
-            const unsigned used = __shfl_sync(FULL, f.y, i);
-            // per-cell word written by classify_scan: case index | offset of the cell's first triangle << 8
-            const unsigned info = bit(used, lane) ? C[(size_t)k * 32 + lane] : 0u;
-            const unsigned code = info & 0xffu;
-            s_code[cl * 32 + lane] = (unsigned char)code;
-            const unsigned nt = (unsigned)(s_case[code] >> 60);
-            const unsigned slot = tb + (info >> 8);
+        const int cl = threadIdx.x >> 2, q4 = threadIdx.x & 3;
+        if (cl < tr.count) {
+            const int k = LISTED ? s_k[cl] : tr.e0 + cl;
+            const uint2 f = __ldg(F + k);
+            const unsigned ub = (f.y >> (8 * q4)) & 0xffu;
+            unsigned codes_lo = 0, codes_hi = 0;
+            if (ub) {
+                // 8 per-cell words = 16 bytes, 16-byte aligned ((32 k + 8 q) * 2)
+                const uint4 cw = __ldg(reinterpret_cast<const uint4 *>(C + (size_t)k * 32 + 8 * q4));
+                const unsigned w[4] = {cw.x, cw.y, cw.z, cw.w};
+                const unsigned tb = f.x - tile_base;
+                const unsigned dbase = ((unsigned)cl << 8) | ((unsigned)q4 << 6);
 #pragma unroll
-            for (unsigned q = 0; q < 5; ++q)
-                if (q < nt) s_list[slot + q] = (unsigned short)((cl << 8) | (lane << 3) | q);
+                for (int j = 0; j < 8; ++j) {
+                    if ((ub >> j) & 1u) {
+                        const unsigned info = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+                        const unsigned code = info & 0xffu;
+                        if (j < 4) codes_lo |= code << (8 * j); else codes_hi |= code << (8 * (j - 4));
+                        const unsigned nt = reinterpret_cast<const unsigned *>(s_case)[2 * code + 1] >> 28;
+                        const unsigned slot = tb + (info >> 8);
+                        const unsigned dd = dbase | ((unsigned)j << 3);
+#pragma unroll
+                        for (unsigned t = 0; t < 5; ++t)
+                            if (t < nt) s_list[slot + t] = (unsigned short)(dd | t);
+                    }
+                }
+            }
+            *reinterpret_cast<uint2 *>(s_code + cl * 32 + 8 * q4) = make_uint2(codes_lo, codes_hi);
         }
     }
     __syncthreads();
@@ -273,9 +315,9 @@ __global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const uint4 
         const unsigned q = d & 7u;
         const int j = (d >> 3) & 31, cl = (d >> 8) & 63;
         const unsigned tri = (unsigned)(s_case[s_code[cl * 32 + j]] >> (12 * q)) & 0xfffu;
-        const long long a = edge_rank(rc, cl, j, tri & 15u);
-        const long long b = edge_rank(rc, cl, j, (tri >> 4) & 15u);
-        const long long c = edge_rank(rc, cl, j, tri >> 8);
+        const long long a = edge_rank<LISTED>(rc, cl, j, tri & 15u);
+        const long long b = edge_rank<LISTED>(rc, cl, j, (tri >> 4) & 15u);
+        const long long c = edge_rank<LISTED>(rc, cl, j, tri >> 8);
         long long *dst = tris + (size_t)(tile_base + i) * 3;
         st_stream(dst, a); st_stream(dst + 1, b); st_stream(dst + 2, c);
     }

@@ -16,7 +16,7 @@ namespace diso {
 
 // MODE 0: quads.  MODE 1: exact adjoint.  MODE 2: reference-compatible adjoint (every patch of a
 // cell reads the adjoint of the cell's FIRST dual vertex, cudualmc.cu:975,990).
-template <typename T, int MODE>
+template <typename T, int MODE, bool LISTED>
 __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const unsigned *__restrict__ S,
                                                               const uint4 *__restrict__ E, const uint4 *__restrict__ P,
                                                               const unsigned short *__restrict__ C,
@@ -29,21 +29,25 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
     __shared__ unsigned s_plen[256];
     __shared__ unsigned s_quad[8];
     __shared__ T s_inv[8];
-    __shared__ int s_k[CT_CHUNKS];
+    __shared__ int s_k[LISTED ? CT_CHUNKS : 1];
     s_case[threadIdx.x] = T_DMC_CASE[threadIdx.x];
     if (MODE != 0) s_plen[threadIdx.x] = T_DMC_PATCHLEN[threadIdx.x];
     if (threadIdx.x < 6) s_quad[threadIdx.x] = T_DMC_QUAD[threadIdx.x];
     if (threadIdx.x < 8) s_inv[threadIdx.x] = threadIdx.x ? T(1) / T((int)threadIdx.x) : T(0);
-    const int count = load_tile_chunks(alist, n_active, s_k);
+    const TileRange<LISTED> tr(alist, n_active);
     unsigned tile_base;
-    const unsigned n = build_edge_list(g, E, s_k, count, s_list, nullptr, tile_base, S);
+    const unsigned n = build_edge_list<LISTED, true>(g, E, tr, S, s_list, nullptr, s_k, tile_base);
     if (n == 0) return;
     __syncthreads();
     for (unsigned i = threadIdx.x; i < n; i += CT_THREADS) {
         const unsigned d = s_list[i];
         const int axis = d & 3, j = (d >> 2) & 31, cl = (d >> 7) & 63, inside = (d >> 13) & 1;
-        const int k = s_k[cl];
-        const unsigned q4 = s_quad[inside * 3 + axis];  // reference dmcQuad[type], type = (exiting ? 3 : 0) + axis
+        const int k = LISTED ? s_k[cl] : tr.e0 + cl;
+        // reference dmcQuad[type], type = (exiting ? 3 : 0) + axis: per corner, the cell at (-dx,-dy,-dz) of the
+        // edge's start point (bits 0..2) and the id of the edge inside that cell (bits 4..7).  Decoded with
+        // ALU ops on purpose: these kernels are bound by L1 / shared-memory wavefronts (a per-corner table in
+        // shared memory measured slower)
+        const unsigned q4 = s_quad[inside * 3 + axis];
         long long id[4];
         Vec3<T> acc{T(0), T(0), T(0)};
 #pragma unroll
@@ -87,20 +91,21 @@ namespace diso {
 constexpr int CT_MAX_PATCHES = CT_CHUNKS * 128;
 
 // ------------------------------------------------------------------------------------------
-// K3d (v2): dual vertices, patch-parallel.  Replaces create_dmc_verts_kernel
+// K3d (v3): dual vertices, patch-parallel.  Replaces create_dmc_verts_kernel
 // (cudualmc.cu:907-955) + epilogue (diso/__init__.py:110-114).
 // The reference recomputes every edge crossing on the fly in each of the 4 cells around the
 // edge (cudualmc.cu:946-948).  Here the crossings are evaluated ONCE by edge_verts_kernel in
 // the raw padded frame into `mcv` (caller scratch, [n_edges,3]) and this kernel only averages:
-//   phase A  lane == cell: the per-cell word written by classify_scan ((possibly complemented)
-//            case index | offset of the cell's first dual vertex) -> one descriptor per patch in
-//            the shared list at slot (dual vertex id - first id of the tile).
+//   phase A  thread == 8 cells of a chunk: the per-cell words written by classify_scan ((possibly
+//            complemented) case index | offset of the cell's first dual vertex), one 128-bit load
+//            -> one descriptor per patch in the shared list at slot (dual vertex id - first id of
+//            the tile); the patch counts come from the record's bit planes (no table lookup).
 //   phase B  thread == dual vertex: gather the crossings of the patch's member edges by rank in
 //            ascending edge id (== the reference's table order, asserted in
 //            tools/extract_tables.py), sum, scale by 1/len, apply the epilogue, store at
 //            consecutive output ranks.  Same values in the same order => bit-identical.
 // ------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool LISTED>
 __global__ void __launch_bounds__(CT_THREADS) dmc_dual_verts_kernel(const T *__restrict__ mcv, Geo g, EpilogueC<T> epi,
                                                                   const uint4 *__restrict__ E,
                                                                   const uint4 *__restrict__ P,
@@ -109,47 +114,52 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_dual_verts_kernel(const T *__r
                                                                   T *__restrict__ verts)
 {
     __shared__ unsigned short s_list[CT_MAX_PATCHES];
-    __shared__ unsigned short s_cell[CT_CHUNKS * 32];
-    __shared__ unsigned s_case[256];
+    __shared__ __align__(16) unsigned short s_cell[CT_CHUNKS * 32];
     __shared__ unsigned s_plen[256];
     __shared__ unsigned long long s_members[256];
     __shared__ uint4 s_E[CT_RECS];
     __shared__ T s_inv[8];
-    __shared__ int s_k[CT_CHUNKS];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int count = load_tile_chunks(alist, n_active, s_k);
-    const unsigned tile_base = P[s_k[0]].x;
-    const unsigned n = P[s_k[count - 1] + 1].x - tile_base;
+    __shared__ int s_k[LISTED ? CT_CHUNKS : 1];
+    const TileRange<LISTED> tr(alist, n_active);
+    const unsigned tile_base = P[tr.kfirst].x;
+    const unsigned n = P[tr.klast + 1].x - tile_base;
     if (n == 0) return;
-    s_case[threadIdx.x] = T_DMC_CASE[threadIdx.x];
     s_plen[threadIdx.x] = T_DMC_PATCHLEN[threadIdx.x];
     s_members[threadIdx.x] = T_DMC_MEMBERS[threadIdx.x];
-    const RecCache rc = load_record_cache(g, E, s_k, count, s_E);
     if (threadIdx.x < 8) s_inv[threadIdx.x] = threadIdx.x ? T(1) / T((int)threadIdx.x) : T(0);
+    if (LISTED) {
+        if ((int)threadIdx.x < tr.count) s_k[threadIdx.x] = tr.chunk(threadIdx.x);
+    }
     __syncthreads();
+    const RecCache<LISTED> rc = load_record_cache<LISTED>(g, E, tr, s_k, s_E);
 
     // ---- phase A ---------------------------------------------------------------------------------
-    constexpr int PER_WARP = CT_CHUNKS / CT_WARPS;
     {
-        const int emine = wid * PER_WARP + lane;
-        const int kmine = (lane < PER_WARP && emine < count) ? s_k[emine] : -1;
-        uint4 pr = make_uint4(0, 0, 0, 0);
-        if (kmine >= 0) pr = P[kmine];
-        unsigned active = __ballot_sync(FULL, pr.y != 0u);
-        while (active) {
-            const int i = __ffs(active) - 1;
-            active &= active - 1;
-            const int cl = wid * PER_WARP + i;
-            const int k = __shfl_sync(FULL, kmine, i);
-            const unsigned pb = __shfl_sync(FULL, pr.x, i) - tile_base;
-            const unsigned used = __shfl_sync(FULL, pr.y, i);
-            const unsigned info = bit(used, lane) ? C[(size_t)k * 32 + lane] : 0u;
-            s_cell[cl * 32 + lane] = (unsigned short)info;
-            const unsigned np = bit(used, lane) ? (s_case[info & 0xffu] >> 24) & 7u : 0u;
-            const unsigned slot = pb + (info >> 8);
+        const int cl = threadIdx.x >> 2, q4 = threadIdx.x & 3;
+        if (cl < tr.count) {
+            const int k = LISTED ? s_k[cl] : tr.e0 + cl;
+            const uint4 pr = __ldg(P + k);
+            const unsigned ub = (pr.y >> (8 * q4)) & 0xffu;
+            if (ub) {
+                const uint4 cw = __ldg(reinterpret_cast<const uint4 *>(C + (size_t)k * 32 + 8 * q4));
+                *reinterpret_cast<uint4 *>(s_cell + cl * 32 + 8 * q4) = cw;
+                const unsigned w[4] = {cw.x, cw.y, cw.z, cw.w};
+                const unsigned lo = pr.z >> (8 * q4), hi = pr.w >> (8 * q4);
+                const unsigned pb = pr.x - tile_base;
+                const unsigned dbase = ((unsigned)cl << 7) | ((unsigned)q4 << 5);
 #pragma unroll
-            for (unsigned q = 0; q < 4; ++q)
-                if (q < np) s_list[slot + q] = (unsigned short)((cl << 7) | (lane << 2) | q);
+                for (int j = 0; j < 8; ++j) {
+                    if ((ub >> j) & 1u) {
+                        const unsigned info = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+                        const unsigned np = 1u + ((lo >> j) & 1u) + 2u * ((hi >> j) & 1u);
+                        const unsigned slot = pb + (info >> 8);
+                        const unsigned dd = dbase | ((unsigned)j << 2);
+#pragma unroll
+                        for (unsigned t = 0; t < 4; ++t)
+                            if (t < np) s_list[slot + t] = (unsigned short)(dd | t);
+                    }
+                }
+            }
         }
     }
     __syncthreads();
@@ -170,7 +180,7 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_dual_verts_kernel(const T *__r
             if (mm) {
                 const int e = __ffs(mm) - 1;
                 mm &= mm - 1;
-                const unsigned r = edge_rank(rc, cl, j, e);
+                const unsigned r = edge_rank<LISTED>(rc, cl, j, e);
                 rank[t] = r;
             }
         }

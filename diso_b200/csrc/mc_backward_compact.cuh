@@ -35,23 +35,31 @@ __global__ void __launch_bounds__(BC_THREADS) mc_backward_compact_kernel(const T
                                                                        const uint4 *__restrict__ E,
                                                                        const T *__restrict__ gsrc,
                                                                        T *__restrict__ adj_sdf,
-                                                                       T *__restrict__ adj_deform, int ntx, int nty)
+                                                                       T *__restrict__ adj_deform, int ntx, int nty, int flat)
 {
     constexpr int BC_ROWS = (BC_X + 1) * (BC_Y + 1);     // candidate rows incl. the -x / -y halo
     constexpr int BC_PTS = BC_X * BC_Y * 32;             // output points per block
-    static_assert(BC_ROWS <= 127 && BC_ROWS <= BC_THREADS, "row index must fit the 7-bit descriptor field");
+    constexpr int BC_ACC = BC_PTS * (HAS_DEF ? 4 : 1);   // accumulators: [BC_PTS] sdf, then [BC_PTS * 3] deform
+    static_assert(BC_ROWS <= 127 && 4 * BC_ROWS <= BC_THREADS, "row index must fit the 7-bit descriptor field; 4 threads per row in step 2");
+    static_assert((BC_ACC * sizeof(T)) % 16 == 0, "accumulators are zeroed with 128-bit stores");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *s_accd = reinterpret_cast<T *>(smem_raw);                       // [BC_PTS]
     T *s_accf = s_accd + BC_PTS;                                       // [BC_PTS * 3] (HAS_DEF only)
-    uint4 *s_rec = reinterpret_cast<uint4 *>(s_accf + (HAS_DEF ? BC_PTS * 3 : 0));  // [BC_ROWS]
-    unsigned *s_off = reinterpret_cast<unsigned *>(s_rec + BC_ROWS);   // [3 * BC_ROWS + 1]
+    uint4 *s_rec = reinterpret_cast<uint4 *>(s_accd + BC_ACC);         // [BC_ROWS]
+    int4 *s_row = reinterpret_cast<int4 *>(s_rec + BC_ROWS);           // [BC_ROWS] {rowbase, flags, xs, ys}
+    unsigned *s_off = reinterpret_cast<unsigned *>(s_row + BC_ROWS);   // [3 * BC_ROWS + 1]
     unsigned *s_zin = s_off + 3 * BC_ROWS + 1;                         // [BC_ROWS] -z halo edge present
     unsigned short *s_list = reinterpret_cast<unsigned short *>(s_zin + BC_ROWS);  // [BC_CAP]
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    int b = blockIdx.x;
-    const int c = b % g.NC; b /= g.NC;
-    const int ty = b % nty; const int tx = b / nty;
+    int c, ty, tx;
+    if (flat) {   // degenerate shapes whose tile counts exceed the y / z grid limits
+        int b = blockIdx.x;
+        c = b % g.NC; b /= g.NC;
+        ty = b % nty; tx = b / nty;
+    } else {
+        c = blockIdx.x; ty = blockIdx.y; tx = blockIdx.z;
+    }
     const int xp0 = 1 + tx * BC_X, yp0 = 1 + ty * BC_Y;  // padded coords of the first output row
 
     // ---- 1. records + counts ---------------------------------------------------------------------
@@ -67,6 +75,9 @@ __global__ void __launch_bounds__(BC_THREADS) mc_backward_compact_kernel(const T
         }
         s_rec[tid] = rec;
         s_zin[tid] = zin;
+        const unsigned fl = (unsigned)(xp >= 1 && xp <= g.X) | ((unsigned)(yp >= 1 && yp <= g.Y) << 1) |
+                            ((unsigned)(xp + 1 <= g.X) << 2) | ((unsigned)(yp + 1 <= g.Y) << 3);
+        s_row[tid] = make_int4(((xp - 1) * g.Y + (yp - 1)) * g.Z + 32 * c - 1, (int)fl, xp, yp);
         s_off[tid] = dyr >= 1 ? __popc(rec.y) : 0;                                   // x-edges: rows with dy >= 0
         s_off[BC_ROWS + tid] = dxr >= 1 ? __popc(rec.z) : 0;                         // y-edges: rows with dx >= 0
         s_off[2 * BC_ROWS + tid] = (dxr >= 1 && dyr >= 1) ? __popc(rec.w) + zin : 0;  // z-edges: output rows
@@ -93,7 +104,7 @@ __global__ void __launch_bounds__(BC_THREADS) mc_backward_compact_kernel(const T
         }
         return;
     }
-    if (wid == 0) {  // exclusive scan of 3*BC_ROWS counts (8 per lane)
+    if (wid == 0) {  // exclusive scan of 3*BC_ROWS counts (a few per lane)
         constexpr int N = 3 * BC_ROWS, PER = (N + 31) / 32;
         unsigned v[PER], sum = 0;
 #pragma unroll
@@ -106,32 +117,47 @@ __global__ void __launch_bounds__(BC_THREADS) mc_backward_compact_kernel(const T
         for (int i = 0; i < PER; ++i) { const int idx = lane * PER + i; if (idx < N) s_off[idx] = run; run += v[i]; }
         if (lane == 31) s_off[N] = inc;
     }
-    // zero the accumulators meanwhile
-    for (int i = tid; i < BC_PTS; i += BC_THREADS) s_accd[i] = T(0);
-    if (HAS_DEF) for (int i = tid; i < BC_PTS * 3; i += BC_THREADS) s_accf[i] = T(0);
+    // zero the accumulators meanwhile (128-bit stores)
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(s_accd);
+        constexpr int NZ = (int)(BC_ACC * sizeof(T) / 16);
+        for (int i = tid; i < NZ; i += BC_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     __syncthreads();
     const unsigned n = s_off[3 * BC_ROWS];
 
     if (n) {
-        // ---- 2. descriptors: {axis:2 | row:7 | lane+1:6} -------------------------------------------
-        const unsigned lt = lanemask_lt(lane);
-        for (int r = wid; r < BC_ROWS; r += BC_THREADS / 32) {
+        // ---- 2. descriptors {axis:2 | row:7 | lane+1:6}: thread == one byte of a row's masks -----------
+        if (tid < 4 * BC_ROWS) {
+            const int r = tid >> 2, sh = (tid & 3) * 8;
             const uint4 rec = s_rec[r];
             const int dxr = r / (BC_Y + 1), dyr = r - dxr * (BC_Y + 1);
-            const unsigned short base = (unsigned short)((r << 6) | (lane + 1));
-            if (dyr >= 1 && bit(rec.y, lane)) s_list[s_off[r] + __popc(rec.y & lt)] = base;
-            if (dxr >= 1 && bit(rec.z, lane)) s_list[s_off[BC_ROWS + r] + __popc(rec.z & lt)] = base | (1u << 13);
-            if (dxr >= 1 && dyr >= 1) {
-                const unsigned zin = s_zin[r];
-                const unsigned o = s_off[2 * BC_ROWS + r];
-                if (zin && lane == 0) s_list[o] = (unsigned short)((r << 6) | 0u | (2u << 13));  // lane -1
-                if (bit(rec.w, lane)) s_list[o + zin + __popc(rec.w & lt)] = base | (2u << 13);
+            const unsigned lt = (1u << sh) - 1u;
+            const unsigned dbase = ((unsigned)r << 6) | (unsigned)(sh + 1);
+            if (dyr >= 1) {
+                unsigned m = (rec.y >> sh) & 0xffu;
+                unsigned slot = s_off[r] + __popc(rec.y & lt);
+                for (; m; m &= m - 1) s_list[slot++] = (unsigned short)(dbase + (unsigned)(__ffs(m) - 1));
+            }
+            if (dxr >= 1) {
+                unsigned m = (rec.z >> sh) & 0xffu;
+                unsigned slot = s_off[BC_ROWS + r] + __popc(rec.z & lt);
+                for (; m; m &= m - 1) s_list[slot++] = (unsigned short)((dbase + (unsigned)(__ffs(m) - 1)) | (1u << 13));
+                if (dyr >= 1) {
+                    const unsigned zin = s_zin[r];
+                    const unsigned o = s_off[2 * BC_ROWS + r];
+                    if (zin && sh == 0) s_list[o] = (unsigned short)(((unsigned)r << 6) | (2u << 13));  // lane -1
+                    m = (rec.w >> sh) & 0xffu;
+                    slot = o + zin + __popc(rec.w & lt);
+                    for (; m; m &= m - 1) s_list[slot++] = (unsigned short)((dbase + (unsigned)(__ffs(m) - 1)) | (2u << 13));
+                }
             }
         }
         __syncthreads();
 
         // ---- 3 + 4. evaluate each edge once, accumulate in conflict-free phases ----------------------
         const unsigned seg1 = s_off[BC_ROWS], seg2 = s_off[2 * BC_ROWS];  // list = [x | y | z]
+        const int sZ = g.Z, sYZ = g.Y * g.Z;
         for (unsigned lo = 0; lo < n; lo += BC_THREADS) {
             const unsigned i = lo + tid;
             int axis = -1, p0 = -1, p1 = -1;
@@ -141,9 +167,9 @@ __global__ void __launch_bounds__(BC_THREADS) mc_backward_compact_kernel(const T
                 const unsigned d = s_list[i];
                 axis = d >> 13;
                 const int r = (d >> 6) & 127, j = (int)(d & 63u) - 1;
-                const int dxr = r / (BC_Y + 1), dyr = r - dxr * (BC_Y + 1);
-                const int xs = xp0 - 1 + dxr, ys = yp0 - 1 + dyr, zs = 32 * c + j;
-                const int xe = xs + (axis == 0), ye = ys + (axis == 1), ze = zs + (axis == 2);
+                const int4 ri = s_row[r];
+                const int xs = ri.z, ys = ri.w, zs = 32 * c + j;
+                const int ze = zs + (axis == 2);
                 const uint4 rec = s_rec[r];
                 unsigned rank;
                 if (j >= 0) {
@@ -155,19 +181,38 @@ __global__ void __launch_bounds__(BC_THREADS) mc_backward_compact_kernel(const T
                     rank = rec.x - 1u;  // +z edge of the previous chunk's last point
                 }
                 const T *gp = gsrc + (size_t)rank * 3;
+#ifdef DISO_GSRC_CS
+                const T gx = __ldcs(gp) * ix, gy = __ldcs(gp + 1) * iy, gz = __ldcs(gp + 2) * iz;
+#else
                 const T gx = __ldg(gp) * ix, gy = __ldg(gp + 1) * iy, gz = __ldg(gp + 2) * iz;
-                const T d0 = fetch_padded(sdf, g, xs, ys, zs, padv);
-                const T d1 = fetch_padded(sdf, g, xe, ye, ze, padv);
-                T p0x = T(xs), p0y = T(ys), p0z = T(zs), p1x = T(xe), p1y = T(ye), p1z = T(ze);
+#endif
+                const unsigned fl = (unsigned)ri.y;
+                const unsigned need1 = axis == 0 ? 6u : (axis == 1 ? 9u : 3u);
+                const bool v0 = (fl & 3u) == 3u && (unsigned)(zs - 1) < (unsigned)g.Z;
+                const bool v1 = (fl & need1) == need1 && (unsigned)(ze - 1) < (unsigned)g.Z;
+                const int i0 = ri.x + j;
+                const int i1 = i0 + (axis == 0 ? sYZ : (axis == 1 ? sZ : 1));
+                const T d0 = v0 ? __ldg(sdf + i0) : padv;
+                const T d1 = v1 ? __ldg(sdf + i1) : padv;
+                // p1 - p0 = unit vector of the axis (+ deformation difference; the pad layer carries none)
+                T dpx = T(axis == 0 ? 1 : 0), dpy = T(axis == 1 ? 1 : 0), dpz = T(axis == 2 ? 1 : 0);
                 if (HAS_DEF) {
-                    const Vec3<T> f0 = fetch_deform(deform, g, xs, ys, zs), f1 = fetch_deform(deform, g, xe, ye, ze);
-                    p0x = p0x + f0.x; p0y = p0y + f0.y; p0z = p0z + f0.z;
-                    p1x = p1x + f1.x; p1y = p1y + f1.y; p1z = p1z + f1.z;
+                    T p0x = T(xs), p0y = T(ys), p0z = T(zs);
+                    T p1x = T(xs + (axis == 0)), p1y = T(ys + (axis == 1)), p1z = T(ze);
+                    if (v0) {
+                        const T *f = deform + (size_t)i0 * 3;
+                        p0x = p0x + __ldg(f); p0y = p0y + __ldg(f + 1); p0z = p0z + __ldg(f + 2);
+                    }
+                    if (v1) {
+                        const T *f = deform + (size_t)i1 * 3;
+                        p1x = p1x + __ldg(f); p1y = p1y + __ldg(f + 1); p1z = p1z + __ldg(f + 2);
+                    }
+                    dpx = p1x - p0x; dpy = p1y - p0y; dpz = p1z - p0z;
                 }
                 const T rr = rcp_fast(d1 - d0);
-                T adj_t = (p1x - p0x) * gx;
-                adj_t = fma_rn(p1y - p0y, gy, adj_t);
-                adj_t = fma_rn(p1z - p0z, gz, adj_t);
+                T adj_t = dpx * gx;
+                adj_t = fma_rn(dpy, gy, adj_t);
+                adj_t = fma_rn(dpz, gz, adj_t);
                 const T s = adj_t * rr * rr;
                 c0d = (iso - d1) * s;
                 c1d = (d0 - iso) * s;
@@ -178,7 +223,7 @@ __global__ void __launch_bounds__(BC_THREADS) mc_backward_compact_kernel(const T
                     c1f = Vec3<T>{t * gx, t * gy, t * gz};
                 }
                 // accumulator slots of the two endpoints (-1: outside this block's output region)
-                const int ox = dxr - 1, oy = dyr - 1;
+                const int ox = xs - xp0, oy = ys - yp0;
                 if (ox >= 0 && oy >= 0 && j >= 0) p0 = (ox * BC_Y + oy) * 32 + j;
                 const int ex = ox + (axis == 0), ey = oy + (axis == 1), ej = j + (axis == 2);
                 if (ex >= 0 && ex < BC_X && ey >= 0 && ey < BC_Y && ej < 32) p1 = (ex * BC_Y + ey) * 32 + ej;
@@ -203,19 +248,31 @@ __global__ void __launch_bounds__(BC_THREADS) mc_backward_compact_kernel(const T
     }
 
     // ---- 5. dense write-out ----------------------------------------------------------------------------
+    const bool zfull = c > 0 && 32 * c + 31 <= g.Z;   // every point of the chunk is a real grid point
     for (int r = wid; r < BC_X * BC_Y; r += BC_THREADS / 32) {
         const int ox = r / BC_Y, oy = r - ox * BC_Y;
         const int xp = xp0 + ox, yp = yp0 + oy;
         if (xp > g.X || yp > g.Y) continue;
         const long long rowb = ((long long)(xp - 1) * g.Y + (yp - 1)) * g.Z + (32 * c - 1);  // element of lane 0
-        const int zp = 32 * c + lane;
-        if (zp >= 1 && zp <= g.Z) st_stream(adj_sdf + rowb + lane, s_accd[r * 32 + lane]);
-        if (HAS_DEF) {
+        T *od = adj_sdf + rowb;
+        T *of = adj_deform + 3 * rowb;
+        if (zfull) {
+            st_stream(od + lane, s_accd[r * 32 + lane]);
+            if (HAS_DEF) {
+                st_stream(of + lane, s_accf[r * 96 + lane]);
+                st_stream(of + lane + 32, s_accf[r * 96 + lane + 32]);
+                st_stream(of + lane + 64, s_accf[r * 96 + lane + 64]);
+            }
+        } else {
+            const int zp = 32 * c + lane;
+            if (zp >= 1 && zp <= g.Z) st_stream(od + lane, s_accd[r * 32 + lane]);
+            if (HAS_DEF) {
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const int e = lane + 32 * q;
-                const int zz = 32 * c + e / 3;
-                if (zz >= 1 && zz <= g.Z) st_stream(adj_deform + 3 * rowb + e, s_accf[r * 96 + e]);
+                for (int q = 0; q < 3; ++q) {
+                    const int e = lane + 32 * q;
+                    const int zz = 32 * c + e / 3;
+                    if (zz >= 1 && zz <= g.Z) st_stream(of + e, s_accf[r * 96 + e]);
+                }
             }
         }
     }
@@ -225,7 +282,7 @@ template <typename T, bool HAS_DEF, int BC_X, int BC_Y> constexpr size_t bwd_com
 {
     constexpr int BC_ROWS = (BC_X + 1) * (BC_Y + 1), BC_PTS = BC_X * BC_Y * 32;
     constexpr int BC_CAP = (BC_X + 1) * BC_Y * 32 + BC_X * (BC_Y + 1) * 32 + BC_X * BC_Y * 33;  // worst-case list length
-    return (size_t)BC_PTS * (HAS_DEF ? 4 : 1) * sizeof(T) + BC_ROWS * sizeof(uint4) + (3 * BC_ROWS + 1 + BC_ROWS) * 4 +
+    return (size_t)BC_PTS * (HAS_DEF ? 4 : 1) * sizeof(T) + BC_ROWS * (sizeof(uint4) + sizeof(int4)) + (3 * BC_ROWS + 1 + BC_ROWS) * 4 +
            (size_t)BC_CAP * 2 + 16;
 }
 
