@@ -165,39 +165,68 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_dual_verts_kernel(const T *__r
     __syncthreads();
 
     // ---- phase B ---------------------------------------------------------------------------------
+    // Vertex ids of all 12 cell edges from 4 records (one per row of the cell): id = B[row][dz] (+ the
+    // lower-axis bits of the owning point), with B[row][1] = B[row][0] + the three bits of point j.  The
+    // member edges are then visited in ascending edge id with compile-time row / axis selectors
+    // (the table-driven loop with a per-edge record decode cost ~2x the instructions, ncu r1_v5).
+    const bool fast = !LISTED || rc.contig;
     for (unsigned i = threadIdx.x; i < n; i += CT_THREADS) {
         const unsigned d = s_list[i];
         const unsigned q = d & 3u;
         const int j = (d >> 2) & 31, cl = (d >> 7) & 63;
         const unsigned code = s_cell[cl * 32 + j] & 0xffu;
         const unsigned plen = s_plen[code];
-        unsigned mm = (unsigned)(s_members[code] >> (12 * q)) & 0xfffu;  // member edges of this patch
-        // pass 1: ranks of the (<= 7) member edges, ascending edge id
-        unsigned rank[7];
-#pragma unroll
-        for (int t = 0; t < 7; ++t) {
-            rank[t] = 0xffffffffu;
-            if (mm) {
-                const int e = __ffs(mm) - 1;
-                mm &= mm - 1;
-                const unsigned r = edge_rank<LISTED>(rc, cl, j, e);
-                rank[t] = r;
-            }
-        }
-        // pass 2: gather + sum in the same (ascending edge id) order
-        T vx[7], vy[7], vz[7];
-#pragma unroll
-        for (int t = 0; t < 7; ++t) {
-            vx[t] = vy[t] = vz[t] = T(0);
-            if (rank[t] != 0xffffffffu) {
-                const T *pv = mcv + (size_t)rank[t] * 3;
-                vx[t] = __ldg(pv); vy[t] = __ldg(pv + 1); vz[t] = __ldg(pv + 2);
-            }
-        }
+        const unsigned mm = (unsigned)(s_members[code] >> (12 * q)) & 0xfffu;  // member edges of this patch
         Vec3<T> acc{T(0), T(0), T(0)};
+        if (fast) {
+            const unsigned l = lanemask_lt(j);
+            unsigned B0[4], B1[4], yb[4], zb[4];
 #pragma unroll
-        for (int t = 0; t < 7; ++t)
-            if (rank[t] != 0xffffffffu) { acc.x = acc.x + vx[t]; acc.y = acc.y + vy[t]; acc.z = acc.z + vz[t]; }
+            for (int rs = 0; rs < 4; ++rs) {
+                const uint4 rec = s_E[rs * (CT_CHUNKS + 1) + cl];
+                B0[rs] = rec.x + __popc(rec.y & l) + __popc(rec.z & l) + __popc(rec.w & l);
+                yb[rs] = (rec.y >> j) & 1u;
+                zb[rs] = (rec.z >> j) & 1u;
+                B1[rs] = B0[rs] + yb[rs] + zb[rs] + ((rec.w >> j) & 1u);
+            }
+            // y-bit of point j+1 in rows 0 and 2 (edges 11 and 10): lane 0 of the next chunk when j == 31
+            unsigned y01, y21;
+            {
+                const int nx = (j + 1) >> 5, jj = (j + 1) & 31;
+                y01 = (s_E[cl + nx].y >> jj) & 1u;
+                y21 = (s_E[2 * (CT_CHUNKS + 1) + cl + nx].y >> jj) & 1u;
+            }
+            unsigned r[12];
+            r[0] = B0[0];                 r[1] = B0[2] + yb[2] + zb[2];  r[2] = B1[0];
+            r[3] = B0[0] + yb[0] + zb[0]; r[4] = B0[1];                  r[5] = B0[3] + yb[3] + zb[3];
+            r[6] = B1[1];                 r[7] = B0[1] + yb[1] + zb[1];  r[8] = B0[0] + yb[0];
+            r[9] = B0[2] + yb[2];         r[10] = B1[2] + y21;           r[11] = B1[0] + y01;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                T vx[6], vy[6], vz[6];
+#pragma unroll
+                for (int t = 0; t < 6; ++t) {
+                    const int e = 6 * h + t;
+                    vx[t] = vy[t] = vz[t] = T(0);
+                    if ((mm >> e) & 1u) {
+                        const T *pv = mcv + (size_t)r[e] * 3;
+                        vx[t] = __ldg(pv); vy[t] = __ldg(pv + 1); vz[t] = __ldg(pv + 2);
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 6; ++t) {
+                    const int e = 6 * h + t;
+                    if ((mm >> e) & 1u) { acc.x = acc.x + vx[t]; acc.y = acc.y + vy[t]; acc.z = acc.z + vz[t]; }
+                }
+            }
+        } else {
+            // scattered tile of a sparse surface: the generic per-edge decode (next-chunk records from global)
+            for (unsigned m2 = mm; m2; m2 &= m2 - 1) {
+                const int e = __ffs(m2) - 1;
+                const T *pv = mcv + (size_t)edge_rank<LISTED>(rc, cl, j, e) * 3;
+                acc.x = acc.x + __ldg(pv); acc.y = acc.y + __ldg(pv + 1); acc.z = acc.z + __ldg(pv + 2);
+            }
+        }
         const T inv = s_inv[(plen >> (4 * q)) & 7u];
         Vec3<T> v{acc.x * inv, acc.y * inv, acc.z * inv};
         v = epi.apply(v);
