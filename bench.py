@@ -10,11 +10,14 @@ with inputs resident in HBM; `e2e` is the same step starting from pinned HOST bu
 and deform every step, D2H of the two losses).  Multi-GPU: one independent 512^3 shape per rank
 (config C5a, seeds differ per rank), no data-path collective -> weak scaling.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size 512] [--kind flexi]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-cpu] [--size 512] [--kind flexi]
 
-`--impl reference`: the reference has NO CPU path and cannot be compiled for the
-CPU, so this arm times the CPU oracle port (oracle/, a restatement of the reference algorithm) on
-all host cores over a bounded sample of the same workload.
+`--impl reference`: the UNMODIFIED reference (baseline/_ref, SarahWeiii/diso v0.1.4 built for sm_100
+by __graft_entry__.build()) through its own public API (diso.DiffMC / diso.DiffDMC), same inputs,
+same harness, same timing code as our arm -- the reference is a CUDA library with NO CPU path
+(SURVEY.md 8c), so its own implementation of the path runs on the GPU.  Its line also carries a
+`cpu_baseline` (the CPU oracle port, oracle/, on a bounded sample).  If baseline/_ref cannot be
+loaded the arm falls back to `--impl reference-cpu`: the oracle port on all host threads.
 """
 import argparse
 import json
@@ -38,7 +41,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--kind", default="flexi", choices=["flexi", "sparse", "dense"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
@@ -156,7 +159,7 @@ def cpu_sample(kind, n, seed, dtype):
     return syn.random_sdf(n, kind, seed, dt).numpy(), syn.random_deform(n, seed + 1, dt).numpy()
 
 
-def run_reference_arm(args, rank, world):
+def run_reference_cpu_arm(args, rank, world, why=None):
     """CPU oracle port on all host cores; bounded sample per step (see module docstring)."""
     if rank != 0:
         return
@@ -184,11 +187,11 @@ def run_reference_arm(args, rank, world):
     dt = time.perf_counter() - t0
     value = vox / dt / 1e9
     sample = "%d concurrent %d^3 crops of the rand-%s workload per step (one per host thread), MC+DMC fwd+bwd each" % (cores, n, args.kind)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "reference_kind": "cpu-oracle-port", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": "C4: random-init %d^3 SDF (rand-%s) + learnable deform, DiffMC and DiffDMC fwd+bwd" % (args.size, args.kind),
-                       "note": "reference has no CPU path; timed: CPU oracle port on a bounded sample"},
+                       "note": "reference has no CPU path; timed: CPU oracle port on a bounded sample" + ((" (fallback: %s)" % why) if why else "")},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -203,9 +206,26 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+    if args.impl == "reference-cpu":
+        run_reference_cpu_arm(args, rank, world)
         return
+    is_ref = args.impl == "reference"
+    ref_mod = None
+    if is_ref:
+        why = None
+        try:
+            import torch
+            from tests.refload import load_reference
+            ref_mod = load_reference()
+            if ref_mod is None:
+                why = "baseline/_ref not loadable"
+            elif not torch.cuda.is_available():
+                why = "no CUDA device"
+        except Exception as ex:
+            why = "%s: %s" % (type(ex).__name__, ex)
+        if why:
+            run_reference_cpu_arm(args, rank, world, why)
+            return
 
     if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
         os.environ.pop("NCCL_DEBUG")        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
@@ -228,7 +248,8 @@ def main():
     def_h = syn.random_deform(n, seed=1000 + rank, dtype=dt).pin_memory()
     sdf_d = sdf_h.to(dev).requires_grad_(True)
     def_d = def_h.to(dev).requires_grad_(True)
-    mods = {"mc": (diso_b200.DiffMC(dt), {}), "dmc": (diso_b200.DiffDMC(dt), dict(return_quads=True))}
+    impl_pkg = ref_mod if is_ref else diso_b200
+    mods = {"mc": (impl_pkg.DiffMC(dt), {}), "dmc": (impl_pkg.DiffDMC(dt), dict(return_quads=True))}
 
     # fixed random dL/dverts per extractor (sizes are deterministic for a fixed input)
     wts, counts = {}, {}
@@ -237,8 +258,8 @@ def main():
             v, f = m(sdf_d, def_d, **kw)
             gen = torch.Generator(device="cpu").manual_seed(7)
             wts[key] = torch.rand(v.shape, generator=gen, dtype=torch.float32).to(dt).to(dev)
-            c = diso_b200.extract_counts(key, sdf_d.detach())
-            counts[key] = dict(verts=v.shape[0], faces=f.shape[0], edges=c["edges"])
+            # crossing edges == MC vertices == DMC quads
+            counts[key] = dict(verts=v.shape[0], faces=f.shape[0], edges=v.shape[0] if key == "mc" else f.shape[0])
             del v, f
     # E = grid points incident to >= 1 crossing edge (for the algorithmic-bytes formula)
     with torch.no_grad():
@@ -280,9 +301,10 @@ def main():
     for _ in range(args.warmup):
         step(sdf_d, def_d)
     sync_all()
-    L0 = _lib.launch_count()
+    import contextlib
+    L0 = 0 if is_ref else _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with _lib.kernel_profile() as prof:
+    with (contextlib.nullcontext() if is_ref else _lib.kernel_profile()) as prof:
         sync_all()
         t_wall0 = time.time()
         e0.record()
@@ -293,7 +315,7 @@ def main():
         t_wall1 = time.time()
     clk.__exit__()
     ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - L0
+    launches = None if is_ref else _lib.launch_count() - L0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -350,28 +372,32 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- per-kernel roofline (dominant kernel, live CUDA-event durations of the timed region) ----
-    per_kernel = {k: sum(v) / len(v) for k, v in prof.times.items()}
-    total_k = {k: sum(v) / args.steps for k, v in prof.times.items()}
-    dom = max(total_k, key=total_k.get)
-    peak, peak_src = peak_hbm()
-    kb = kernel_bytes(dom, G, s_bytes, counts["mc"], counts["dmc"], True)
-    achieved = kb / (per_kernel[dom] * 1e-3) / 1e9
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get("%s@%d^3-%s-%s" % (dom, n, args.kind, args.dtype))
-    except Exception:
-        pass
     fwd_mc, bwd_mc = algorithmic_bytes(G, s_bytes, counts["mc"]["verts"], counts["mc"]["faces"], 3, endpoints, True)
     fwd_d, bwd_d = algorithmic_bytes(G, s_bytes, counts["dmc"]["verts"], counts["dmc"]["faces"], 4, endpoints, True)
     step_bytes = fwd_mc + bwd_mc + fwd_d + bwd_d
     ms_step = ms_max / args.steps
-    kernels = {}
-    for k in sorted(total_k, key=total_k.get, reverse=True):
-        b_ = kernel_bytes(k, G, s_bytes, counts["mc"], counts["dmc"], True)
-        kernels[k] = {"ms": round(per_kernel[k], 4), "share_of_step": round(total_k[k] / ms_step, 4),
-                      "alg_GBps": round(b_ / (per_kernel[k] * 1e-3) / 1e9, 1) if b_ else None}
+    peak, peak_src = peak_hbm()
+    roofline, kernels = None, {}
+    if not is_ref:
+        # ---- per-kernel roofline (dominant kernel, live CUDA-event durations of the timed region) ----
+        per_kernel = {k: sum(v) / len(v) for k, v in prof.times.items()}
+        total_k = {k: sum(v) / args.steps for k, v in prof.times.items()}
+        dom = max(total_k, key=total_k.get)
+        kb = kernel_bytes(dom, G, s_bytes, counts["mc"], counts["dmc"], True)
+        achieved = kb / (per_kernel[dom] * 1e-3) / 1e9
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get("%s@%d^3-%s-%s" % (dom, n, args.kind, args.dtype))
+        except Exception:
+            pass
+        for k in sorted(total_k, key=total_k.get, reverse=True):
+            b_ = kernel_bytes(k, G, s_bytes, counts["mc"], counts["dmc"], True)
+            kernels[k] = {"ms": round(per_kernel[k], 4), "launches_per_step": round(len(prof.times[k]) / args.steps, 2),
+                          "share_of_step": round(total_k[k] / ms_step, 4),
+                          "alg_GBps": round(b_ / (per_kernel[k] * 1e-3) / 1e9, 1) if b_ else None}
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "kernel_ms": per_kernel[dom], "kernel_alg_bytes": kb}
 
     line = {
         "metric": METRIC, "value": world * 2 * G / (ms_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
@@ -383,19 +409,23 @@ def main():
         "clocks": clk.summary(t_wall0, t_wall1),
         "e2e": {"value": world * 2 * G / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(sdf_h.numel() * s_bytes + def_h.numel() * s_bytes), "d2h_bytes_per_step": 2 * s_bytes},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel_ms": per_kernel[dom], "kernel_alg_bytes": kb},
+        "gpu_launches": launches,
+        "roofline": roofline,
         "step_roofline": {"alg_bytes_per_step": step_bytes, "achieved_GBps": step_bytes / (ms_step * 1e-3) / 1e9,
                           "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
         "kernels": kernels,
         "mesh": {"mc": counts["mc"], "dmc": counts["dmc"]},
     }
 
+    if is_ref:
+        line["impl"] = "reference"
+        line["reference_kind"] = "unmodified SarahWeiii/diso v0.1.4 CUDA build (baseline/_ref, sm_100) through diso.DiffMC / diso.DiffDMC"
+        line.pop("gpu_launches")      # not ours to count
+        line.pop("kernels")
     # ---- CPU baseline (rank 0, N=1): single-threaded oracle port on a bounded sample --------------
     if world == 1 and not args.no_cpu_baseline:
         try:
-            ncpu = 128
+            ncpu = 320   # ~10-15 s of single-threaded CPU work
             smp = cpu_sample(args.kind, ncpu, 0, args.dtype)
             t0 = time.perf_counter()
             vox = oracle_pass(*smp)
@@ -407,7 +437,7 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "failed: %s" % ex}
 
     # ---- reference CUDA build on the same GPU, same harness (reported beside ours; N=1 only) ------
-    if world == 1 and not args.no_ref_cuda:
+    if world == 1 and not args.no_ref_cuda and not is_ref:
         try:
             from tests.refload import load_reference
             ref = load_reference()

@@ -258,7 +258,10 @@ int launch_bwd_compact(const T *sdf, const T *deform, const Geo &g, T isoT, T pa
     auto kern = mc_backward_compact_kernel<T, HAS_DEF, BX, BY>;
     static const int smem_pad = env_int("DISO_BWD_SMEM_PAD", 0);   // experiment knob: caps the CTAs per SM
     const size_t smem = bwd_compact_smem<T, HAS_DEF, BX, BY>() + (size_t)smem_pad;
-    kernel_attrs(reinterpret_cast<const void *>(kern), "DISO_CARVEOUT_BWD", 58, smem);
+    // L1 capacity matters more than occupancy here (the gathers of sdf / deform / adjoints hit L1 ~63 %): with the
+    // driver's default carve-out (8 CTAs/SM, ~28 KB L1) the fp32 kernel takes 2.48 ms at 512^3, with 132 KB of
+    // shared memory (5 CTAs, ~124 KB L1) 1.72 ms; fp64: 3.18 ms at 72 % vs 4.59 ms at 100 % (sweeps in DESIGN.md)
+    kernel_attrs(reinterpret_cast<const void *>(kern), "DISO_CARVEOUT_BWD", sizeof(T) == 4 ? 58 : 72, smem);
     const int ntx = cdiv(g.X, BX), nty = cdiv(g.Y, BY);
     // 3-D grid (chunk, y tile, x tile): no index divisions in the kernel; shapes whose tile counts exceed
     // the 65535 limit of grid.y / grid.z fall back to a flat grid decoded with divisions

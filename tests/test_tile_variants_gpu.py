@@ -1,0 +1,69 @@
+"""The emit / adjoint kernels exist in two tile flavours (diso_b200/csrc/compact.cuh): "dense" tiles
+of 64 consecutive chunks and "listed" tiles over the ordered active-chunk list (sparse surfaces).
+The host picks one from the counts; both must produce identical bits.  Called through the C ABI:
+counts_host == NULL forces the dense flavour, the counts read back after phase 1 select the listed
+one whenever fewer than 75 % of the chunks are active."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def blobs(n, seed):
+    """A few small spheres scattered in an otherwise empty grid: scattered (non-contiguous) tiles."""
+    g = torch.Generator().manual_seed(seed)
+    ax = torch.arange(n, dtype=torch.float32)
+    x, y, z = torch.meshgrid(ax, ax, ax, indexing="ij")
+    sdf = torch.full((n, n, n), 10.0)
+    for _ in range(7):
+        c = torch.rand(3, generator=g) * (n - 8) + 4
+        r = 2.0 + 3.0 * float(torch.rand(1, generator=g))
+        sdf = torch.minimum(sdf, ((x - c[0]) ** 2 + (y - c[1]) ** 2 + (z - c[2]) ** 2).sqrt() - r)
+    return sdf + 0.013 * torch.rand(sdf.shape, generator=g)
+
+
+@pytest.mark.parametrize("alg", ["mc", "dmc"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_dense_and_listed_tiles_agree(alg, dtype):
+    import diso_b200
+    from diso_b200 import _lib
+    L = _lib.load()
+    n = 70
+    sdf = blobs(n, 3).to(dtype).to(DEV)
+    deform = (0.4 * torch.tanh(torch.randn(n, n, n, 3, generator=torch.Generator().manual_seed(5)))).to(dtype).to(DEV)
+    alg_id = _lib.ALG_MC if alg == "mc" else _lib.ALG_DMC
+    dt = _lib.F32 if dtype == torch.float32 else _lib.F64
+    state, counts = diso_b200._count(alg_id, sdf, 0.0)
+    lay = (ctypes.c_int64 * 8)()
+    _lib.check(L.diso_b200_state_layout(alg_id, n, n, n, lay))
+    nch = lay[5]
+    assert 0 < counts[_lib.CNT_EDGE_CHUNKS] * 4 < nch * 3 and 0 < counts[_lib.CNT_CELL_CHUNKS] * 4 < nch * 3, "input must select the listed flavour"
+    nv, nf = counts[_lib.CNT_VERTS], counts[_lib.CNT_FACES]
+    k = 3 if alg == "mc" else 4
+    ne = nv if alg == "mc" else nf
+    st = torch.cuda.current_stream().cuda_stream
+    res = []
+    for ch in (ctypes.cast(_lib.counts_array(counts), ctypes.c_void_p), None):
+        verts = torch.full((nv, 3), float("nan"), dtype=dtype, device=DEV)
+        faces = torch.full((nf, k), -1, dtype=torch.int64, device=DEV)
+        adj_s = torch.full_like(sdf, float("nan"))
+        adj_d = torch.full_like(deform, float("nan"))
+        w = torch.cos(torch.arange(nv * 3, dtype=torch.float64).reshape(nv, 3) * 0.618).to(dtype).to(DEV)
+        common = (sdf.data_ptr(), deform.data_ptr(), dt, n, n, n, 0.0, state.data_ptr())
+        if alg == "mc":
+            _lib.check(L.diso_b200_mc_emit(*common, ch, 1, verts.data_ptr(), faces.data_ptr(), st))
+            _lib.check(L.diso_b200_mc_backward(*common, w.data_ptr(), 1, adj_s.data_ptr(), adj_d.data_ptr(), st))
+        else:
+            scratch = torch.empty((ne, 3), dtype=dtype, device=DEV)
+            _lib.check(L.diso_b200_dmc_emit(*common, ch, 1, scratch.data_ptr(), verts.data_ptr(), faces.data_ptr(), st))
+            for gm in (_lib.GRAD_REFERENCE, _lib.GRAD_EXACT):
+                _lib.check(L.diso_b200_dmc_backward(*common, ch, w.data_ptr(), 1, gm, scratch.data_ptr(), adj_s.data_ptr(), adj_d.data_ptr(), st))
+        torch.cuda.synchronize()
+        res.append([t.cpu().numpy() for t in (verts, faces, adj_s, adj_d)])
+    for a, b, what in zip(res[0], res[1], ("verts", "faces", "adj_sdf", "adj_deform")):
+        assert not np.isnan(a.astype(np.float64)).any() and (a != -1).any(), what + ": not fully written"
+        assert np.array_equal(a, b), what + ": listed and dense tile flavours differ"
