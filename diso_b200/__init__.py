@@ -70,8 +70,11 @@ class _Extract(Function):
     keeps batch / activation-checkpoint semantics (nothing lives in the extractor object)."""
 
     @staticmethod
-    def forward(ctx, grid, deform, alg, isovalue, normalize, grad_mode, state, counts):
+    def forward(ctx, grid, deform, alg, isovalue, normalize, grad_mode, state, counts, frame=None):
+        # frame: None, or (x_origin, X_global, id_offset) when `grid` is a slab of a larger grid
+        # (diso_b200/parallel.py): vertices come out in the global frame, faces with global ids
         L = _lib.load()
+        ctx.frame = _lib.Frame(*[int(v) for v in frame]) if frame is not None else None
         X, Y, Z = grid.shape
         k = 3 if alg == _lib.ALG_MC else 4
         n_verts, n_faces = counts[_lib.CNT_VERTS], counts[_lib.CNT_FACES]
@@ -79,7 +82,7 @@ class _Extract(Function):
         verts = torch.empty((n_verts, 3), dtype=grid.dtype, device=grid.device)
         faces = torch.empty((n_faces, k), dtype=torch.int64, device=grid.device)
         args = (grid.data_ptr(), _ptr(deform), _DTYPES[grid.dtype], X, Y, Z, float(isovalue), state.data_ptr(),
-                ctypes.cast(ctx.counts, ctypes.c_void_p), int(bool(normalize)))
+                ctypes.cast(ctx.counts, ctypes.c_void_p), int(bool(normalize)), _lib.frame_ptr(ctx.frame))
         if alg == _lib.ALG_MC:
             _lib.check(L.diso_b200_mc_emit(*args, verts.data_ptr(), faces.data_ptr(), _stream()))
         else:
@@ -100,7 +103,7 @@ class _Extract(Function):
         X, Y, Z = grid.shape
         if adj_verts is None:  # verts did not take part in the loss: all gradients are zero
             return (torch.zeros_like(grid), torch.zeros_like(deform) if deform is not None else None,
-                    None, None, None, None, None, None)
+                    None, None, None, None, None, None, None)
         # the reference requires a contiguous adj_verts and raises otherwise (pybind.cpp:142);
         # expanded gradients (e.g. from verts.sum() with normalize=False) are made contiguous here.
         adj_verts = adj_verts.contiguous()
@@ -112,16 +115,16 @@ class _Extract(Function):
             if ctx.alg == _lib.ALG_MC:
                 _lib.check(L.diso_b200_mc_backward(grid.data_ptr(), _ptr(deform), dt, X, Y, Z, ctx.isovalue,
                                                    state.data_ptr(), adj_verts.data_ptr(), int(ctx.normalize),
-                                                   adj_grid.data_ptr(), _ptr(adj_deform), _stream()))
+                                                   _lib.frame_ptr(ctx.frame), adj_grid.data_ptr(), _ptr(adj_deform), _stream()))
             else:
                 scratch = torch.empty((max(ctx.n_edges, 1), 3), dtype=grid.dtype, device=grid.device)
                 _lib.check(L.diso_b200_dmc_backward(grid.data_ptr(), _ptr(deform), dt, X, Y, Z, ctx.isovalue,
                                                     state.data_ptr(), ctypes.cast(ctx.counts, ctypes.c_void_p),
-                                                    adj_verts.data_ptr(), int(ctx.normalize),
+                                                    adj_verts.data_ptr(), int(ctx.normalize), _lib.frame_ptr(ctx.frame),
                                                     ctx.grad_mode, scratch.data_ptr(), adj_grid.data_ptr(),
                                                     _ptr(adj_deform), _stream()))
         del need_grid
-        return adj_grid, adj_deform, None, None, None, None, None, None
+        return adj_grid, adj_deform, None, None, None, None, None, None, None
 
 
 def _run(alg, dtype, grad_mode, grid, deform, isovalue, normalize, want_state=False, slab_mode=False):

@@ -18,6 +18,16 @@ COUNT_SLOTS = 8
 CNT_VERTS, CNT_FACES, CNT_ANY_GT, CNT_EDGES, CNT_USED, CNT_EDGE_CHUNKS, CNT_CELL_CHUNKS = 0, 1, 2, 3, 4, 5, 6
 
 
+class Frame(ctypes.Structure):
+    """diso_b200_frame (include/diso_b200.h): a slab's place inside a larger grid."""
+    _fields_ = [("x_origin", ctypes.c_int32), ("X_global", ctypes.c_int32), ("id_offset", ctypes.c_int64)]
+
+
+def frame_ptr(frame):
+    """None or a Frame -> the void* the C ABI takes (keep the Frame alive while the call runs)."""
+    return None if frame is None else ctypes.cast(ctypes.pointer(frame), ctypes.c_void_p)
+
+
 def counts_array(counts):
     """ctypes int64[COUNT_SLOTS] holding the host copy of the count block (passed to emit / backward)."""
     return (ctypes.c_int64 * COUNT_SLOTS)(*[int(c) for c in counts])
@@ -30,10 +40,10 @@ SIGNATURES = {
     "diso_b200_state_bytes": (_sz, [_i, _i, _i, _i]),
     "diso_b200_state_layout": (_i, [_i, _i, _i, _i, ctypes.POINTER(ctypes.c_int64)]),
     "diso_b200_count": (_i, [_i, _vp, _i, _i, _i, _i, _d, _vp, _sz, _vp]),
-    "diso_b200_mc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp]),
-    "diso_b200_dmc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
-    "diso_b200_mc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp]),
-    "diso_b200_dmc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "diso_b200_mc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "diso_b200_dmc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "diso_b200_mc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "diso_b200_dmc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "diso_b200_quad_split_scratch_bytes": (_sz, [_i64]),
     "diso_b200_quad_split": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp]),
     "diso_b200_debug_cell_codes": (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
@@ -62,7 +72,7 @@ def load():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.diso_b200_abi_version() != 1:
+        if L.diso_b200_abi_version() != 2:
             raise DisoB200Error("libdiso_b200.so ABI version mismatch")
         _lib = L
     return _lib

@@ -81,13 +81,23 @@ StatePtrs state_ptrs(void *state, const StateLayout &L)
     return p;
 }
 
-template <typename T> EpilogueC<T> make_epilogue_c(const Geo &g, int normalize, bool shift = true)
+// Frame of a slab inside a larger grid (diso_b200_frame; standalone: x_origin 0, X_global X, id_offset 0)
+struct Frame { int x_origin; int X_global; long long id_offset; };
+inline Frame make_frame(const diso_b200_frame *f, int X)
+{
+    Frame r{0, X, 0};
+    if (f) { r.x_origin = f->x_origin; r.X_global = f->X_global > 0 ? f->X_global : X; r.id_offset = (long long)f->id_offset; }
+    return r;
+}
+
+template <typename T> EpilogueC<T> make_epilogue_c(const Geo &g, const Frame &fr, int normalize, bool shift = true)
 {
     EpilogueC<T> e;
-    e.dx = T(g.X) - T(1); e.dy = T(g.Y) - T(1); e.dz = T(g.Z) - T(1);
+    e.dx = T(fr.X_global) - T(1); e.dy = T(g.Y) - T(1); e.dz = T(g.Z) - T(1);
     e.rx = T(1) / e.dx; e.ry = T(1) / e.dy; e.rz = T(1) / e.dz;
-    const bool zero_div = g.X == 1 || g.Y == 1 || g.Z == 1;
+    const bool zero_div = fr.X_global == 1 || g.Y == 1 || g.Z == 1;
     e.normalize = !shift ? 0 : (normalize ? (zero_div ? 3 : 2) : 1);
+    e.x0 = fr.x_origin;
     return e;
 }
 
@@ -203,10 +213,10 @@ int count_impl(int alg, const T *sdf, const Geo &g, double iso, const StateLayou
 
 template <typename T>
 int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const int64_t *counts_host,
-                 int normalize, T *verts, long long *tris, cudaStream_t st)
+                 int normalize, const Frame &fr, T *verts, long long *tris, cudaStream_t st)
 {
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
-    const EpilogueC<T> epi = make_epilogue_c<T>(g, normalize);
+    const EpilogueC<T> epi = make_epilogue_c<T>(g, fr, normalize);
     const TileGrid te = tile_grid(p, g, counts_host, 0), tc = tile_grid(p, g, counts_host, 1);
     kernel_attrs(reinterpret_cast<const void *>(edge_verts_kernel<T, true>), "DISO_CARVEOUT_EV", -1);
     kernel_attrs(reinterpret_cast<const void *>(edge_verts_kernel<T, false>), "DISO_CARVEOUT_EV", -1);
@@ -216,19 +226,19 @@ int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const 
     }
     if (tc.ctas) {
         const uint2 *F = reinterpret_cast<const uint2 *>(p.aux);
-        if (tc.list) LAUNCH("mc_emit_tris", st, mc_tris_kernel<true><<<tc.ctas, CT_THREADS, 0, st>>>(g, p.E, F, p.C, tc.list, tc.n_active, tris));
-        else LAUNCH("mc_emit_tris", st, mc_tris_kernel<false><<<tc.ctas, CT_THREADS, 0, st>>>(g, p.E, F, p.C, tc.list, tc.n_active, tris));
+        if (tc.list) LAUNCH("mc_emit_tris", st, mc_tris_kernel<true><<<tc.ctas, CT_THREADS, 0, st>>>(g, p.E, F, p.C, tc.list, tc.n_active, fr.id_offset, tris));
+        else LAUNCH("mc_emit_tris", st, mc_tris_kernel<false><<<tc.ctas, CT_THREADS, 0, st>>>(g, p.E, F, p.C, tc.list, tc.n_active, fr.id_offset, tris));
     }
     return DISO_OK;
 }
 
 template <typename T>
 int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const int64_t *counts_host,
-                  int normalize, T *scratch, T *verts, long long *quads, cudaStream_t st)
+                  int normalize, const Frame &fr, T *scratch, T *verts, long long *quads, cudaStream_t st)
 {
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
-    const EpilogueC<T> raw = make_epilogue_c<T>(g, 0, false), epic = make_epilogue_c<T>(g, normalize);
+    const EpilogueC<T> raw = make_epilogue_c<T>(g, fr, 0, false), epic = make_epilogue_c<T>(g, fr, normalize);
     const TileGrid te = tile_grid(p, g, counts_host, 0), tc = tile_grid(p, g, counts_host, 1);
     kernel_attrs(reinterpret_cast<const void *>(edge_verts_kernel<T, true>), "DISO_CARVEOUT_EV", -1);
     kernel_attrs(reinterpret_cast<const void *>(edge_verts_kernel<T, false>), "DISO_CARVEOUT_EV", -1);
@@ -245,8 +255,8 @@ int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const
         else LAUNCH("dmc_emit_verts", st, (dmc_dual_verts_kernel<T, false><<<tc.ctas, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, tc.list, tc.n_active, verts)));
     }
     if (te.ctas) {
-        if (te.list) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, true><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, quads, nullptr)));
-        else LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, false><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, quads, nullptr)));
+        if (te.list) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, true><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, fr.id_offset, quads, nullptr)));
+        else LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, false><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, fr.id_offset, quads, nullptr)));
     }
     return DISO_OK;
 }
@@ -274,11 +284,11 @@ int launch_bwd_compact(const T *sdf, const T *deform, const Geo &g, T isoT, T pa
 
 template <typename T>
 int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const T *adj_verts,
-                     int normalize, T *adj_sdf, T *adj_deform, cudaStream_t st)
+                     int normalize, int X_global, T *adj_sdf, T *adj_deform, cudaStream_t st)
 {
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     // chain rule of verts / (dims - 1): multiply by the reciprocal (gradients carry a 1e-5 bar, not bit parity)
-    const T ix = normalize ? T(1) / (T(g.X) - T(1)) : T(1), iy = normalize ? T(1) / (T(g.Y) - T(1)) : T(1),
+    const T ix = normalize ? T(1) / (T(X_global) - T(1)) : T(1), iy = normalize ? T(1) / (T(g.Y) - T(1)) : T(1),
             iz = normalize ? T(1) / (T(g.Z) - T(1)) : T(1);
     // block shape from a sweep on B200 (512^3 rand-flexi): 4x8 1.90 ms, 8x4 1.94, 8x8 2.05, 4x4 2.21
 #ifdef DISO_TUNE
@@ -304,19 +314,19 @@ int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, co
 
 template <typename T>
 int dmc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const int64_t *counts_host,
-                      const T *adj_verts, int normalize, int grad_mode, T *scratch, T *adj_sdf, T *adj_deform, cudaStream_t st)
+                      const T *adj_verts, int normalize, int X_global, int grad_mode, T *scratch, T *adj_sdf, T *adj_deform, cudaStream_t st)
 {
     const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
-    const T ix = normalize ? T(1) / (T(g.X) - T(1)) : T(1), iy = normalize ? T(1) / (T(g.Y) - T(1)) : T(1),
+    const T ix = normalize ? T(1) / (T(X_global) - T(1)) : T(1), iy = normalize ? T(1) / (T(g.Y) - T(1)) : T(1),
             iz = normalize ? T(1) / (T(g.Z) - T(1)) : T(1);
     const TileGrid te = tile_grid(p, g, counts_host, 0);
     if (te.ctas) {
-#define DISO_ADJ(MODE, LISTED) { kernel_attrs(reinterpret_cast<const void *>(dmc_edges2_kernel<T, MODE, LISTED>), "DISO_CARVEOUT_ADJ", -1); LAUNCH("dmc_edge_adjoint", st, (dmc_edges2_kernel<T, MODE, LISTED><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, ix, iy, iz, adj_verts, nullptr, scratch))); }
+#define DISO_ADJ(MODE, LISTED) { kernel_attrs(reinterpret_cast<const void *>(dmc_edges2_kernel<T, MODE, LISTED>), "DISO_CARVEOUT_ADJ", -1); LAUNCH("dmc_edge_adjoint", st, (dmc_edges2_kernel<T, MODE, LISTED><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, ix, iy, iz, adj_verts, 0ll, nullptr, scratch))); }
         if (grad_mode == DISO_GRAD_EXACT) { if (te.list) DISO_ADJ(1, true) else DISO_ADJ(1, false) }
         else                              { if (te.list) DISO_ADJ(2, true) else DISO_ADJ(2, false) }
 #undef DISO_ADJ
     }
-    return mc_backward_impl<T>(sdf, deform, g, iso, p, scratch, 0, adj_sdf, adj_deform, st);
+    return mc_backward_impl<T>(sdf, deform, g, iso, p, scratch, 0, g.X, adj_sdf, adj_deform, st);
 }
 
 }  // namespace
@@ -396,61 +406,66 @@ int diso_b200_count(int alg, const void *sdf, int dtype, int X, int Y, int Z, do
 }
 
 int diso_b200_mc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
-                      const void *state, const int64_t *counts_host, int normalize, void *verts, int64_t *tris, void *stream)
+                      const void *state, const int64_t *counts_host, int normalize, const diso_b200_frame *frame,
+                      void *verts, int64_t *tris, void *stream)
 {
     int rc = check_dims(DISO_ALG_MC, dtype, X, Y, Z);
     if (rc) return rc;
     if (!sdf || !state || !verts || !tris) return fail(DISO_E_INVALID, "null pointer");
     const Geo g = make_geo(X, Y, Z);
+    const Frame fr = make_frame(frame, X);
     const StatePtrs p = state_ptrs(const_cast<void *>(state), make_layout(DISO_ALG_MC, g));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == DISO_F32)
-        return mc_emit_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, counts_host, normalize,
+        return mc_emit_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, counts_host, normalize, fr,
                                    static_cast<float *>(verts), reinterpret_cast<long long *>(tris), st);
-    return mc_emit_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, counts_host, normalize,
+    return mc_emit_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, counts_host, normalize, fr,
                                 static_cast<double *>(verts), reinterpret_cast<long long *>(tris), st);
 }
 
 int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
-                       const void *state, const int64_t *counts_host, int normalize, void *scratch, void *verts,
-                       int64_t *quads, void *stream)
+                       const void *state, const int64_t *counts_host, int normalize, const diso_b200_frame *frame,
+                       void *scratch, void *verts, int64_t *quads, void *stream)
 {
     int rc = check_dims(DISO_ALG_DMC, dtype, X, Y, Z);
     if (rc) return rc;
     if (!sdf || !state || !scratch || !verts || !quads) return fail(DISO_E_INVALID, "null pointer");
     const Geo g = make_geo(X, Y, Z);
+    const Frame fr = make_frame(frame, X);
     const StatePtrs p = state_ptrs(const_cast<void *>(state), make_layout(DISO_ALG_DMC, g));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == DISO_F32)
-        return dmc_emit_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, counts_host, normalize,
+        return dmc_emit_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, counts_host, normalize, fr,
                                     static_cast<float *>(scratch), static_cast<float *>(verts), reinterpret_cast<long long *>(quads), st);
-    return dmc_emit_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, counts_host, normalize,
+    return dmc_emit_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, counts_host, normalize, fr,
                                  static_cast<double *>(scratch), static_cast<double *>(verts), reinterpret_cast<long long *>(quads), st);
 }
 
 int diso_b200_mc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
-                          const void *state, const void *adj_verts, int normalize, void *adj_sdf, void *adj_deform,
-                          void *stream)
+                          const void *state, const void *adj_verts, int normalize, const diso_b200_frame *frame,
+                          void *adj_sdf, void *adj_deform, void *stream)
 {
     int rc = check_dims(DISO_ALG_MC, dtype, X, Y, Z);
     if (rc) return rc;
     if (!sdf || !state || !adj_verts || !adj_sdf) return fail(DISO_E_INVALID, "null pointer");
     if ((deform == nullptr) != (adj_deform == nullptr)) return fail(DISO_E_INVALID, "deform and adj_deform must both be given or both be NULL");
     const Geo g = make_geo(X, Y, Z);
+    const Frame fr = make_frame(frame, X);
     const StatePtrs p = state_ptrs(const_cast<void *>(state), make_layout(DISO_ALG_MC, g));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == DISO_F32)
         return mc_backward_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p,
-                                       static_cast<const float *>(adj_verts), normalize, static_cast<float *>(adj_sdf),
+                                       static_cast<const float *>(adj_verts), normalize, fr.X_global, static_cast<float *>(adj_sdf),
                                        static_cast<float *>(adj_deform), st);
     return mc_backward_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p,
-                                    static_cast<const double *>(adj_verts), normalize, static_cast<double *>(adj_sdf),
+                                    static_cast<const double *>(adj_verts), normalize, fr.X_global, static_cast<double *>(adj_sdf),
                                     static_cast<double *>(adj_deform), st);
 }
 
 int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
                            const void *state, const int64_t *counts_host, const void *adj_verts, int normalize,
-                           int grad_mode, void *scratch, void *adj_sdf, void *adj_deform, void *stream)
+                           const diso_b200_frame *frame, int grad_mode, void *scratch, void *adj_sdf, void *adj_deform,
+                           void *stream)
 {
     int rc = check_dims(DISO_ALG_DMC, dtype, X, Y, Z);
     if (rc) return rc;
@@ -458,14 +473,15 @@ int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X
     if ((deform == nullptr) != (adj_deform == nullptr)) return fail(DISO_E_INVALID, "deform and adj_deform must both be given or both be NULL");
     if (grad_mode != DISO_GRAD_REFERENCE && grad_mode != DISO_GRAD_EXACT) return fail(DISO_E_INVALID, "unknown grad_mode %d", grad_mode);
     const Geo g = make_geo(X, Y, Z);
+    const Frame fr = make_frame(frame, X);
     const StatePtrs p = state_ptrs(const_cast<void *>(state), make_layout(DISO_ALG_DMC, g));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == DISO_F32)
         return dmc_backward_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, counts_host,
-                                        static_cast<const float *>(adj_verts), normalize, grad_mode, static_cast<float *>(scratch),
+                                        static_cast<const float *>(adj_verts), normalize, fr.X_global, grad_mode, static_cast<float *>(scratch),
                                         static_cast<float *>(adj_sdf), static_cast<float *>(adj_deform), st);
     return dmc_backward_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, counts_host,
-                                     static_cast<const double *>(adj_verts), normalize, grad_mode, static_cast<double *>(scratch),
+                                     static_cast<const double *>(adj_verts), normalize, fr.X_global, grad_mode, static_cast<double *>(scratch),
                                      static_cast<double *>(adj_sdf), static_cast<double *>(adj_deform), st);
 }
 

@@ -125,6 +125,8 @@ template <typename T> struct EpilogueC {
     T rx, ry, rz;  // RN(1 / (dim - 1))
     int normalize; // 0: raw padded frame (no shift), 1: (p-1), 2: (p-1)/(dim-1) via div_by_const,
                    // 3: (p-1)/(dim-1) by plain division (some dim == 1, i.e. a zero divisor)
+    int x0;        // slab frame: global index of the local grid's first x layer (added to the integer
+                   // x coordinate BEFORE the deformation, so a slab reproduces the whole grid's bits)
     __device__ __forceinline__ Vec3<T> apply(Vec3<T> p) const
     {
         if (normalize == 0) return p;
@@ -173,8 +175,9 @@ __global__ void __launch_bounds__(CT_THREADS) edge_verts_kernel(const T *__restr
         const T d0 = v0 ? __ldg(sdf + i0) : padv;
         const T d1 = v1 ? __ldg(sdf + i1) : padv;
         const T t = edge_t(d0, d1, iso);
-        Vec3<T> p0{T((int)tp.xp), T((int)tp.yp), T(zp)};
-        Vec3<T> p1{T((int)tp.xp + (axis == 0)), T((int)tp.yp + (axis == 1)), T(zq)};
+        const int xg = (int)tp.xp + epi.x0;
+        Vec3<T> p0{T(xg), T((int)tp.yp), T(zp)};
+        Vec3<T> p1{T(xg + (axis == 0)), T((int)tp.yp + (axis == 1)), T(zq)};
         if (has_def) {
             // the pad layer carries zero deformation (diso/__init__.py:54)
             if (v0) {
@@ -260,7 +263,7 @@ template <bool LISTED>
 __global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const uint4 *__restrict__ E, const uint2 *__restrict__ F,
                                                            const unsigned short *__restrict__ C,
                                                            const unsigned *__restrict__ alist, int n_active,
-                                                           long long *__restrict__ tris)
+                                                           long long id_offset, long long *__restrict__ tris)
 {
     __shared__ unsigned long long s_case[256];
     __shared__ uint4 s_E[CT_RECS];
@@ -315,9 +318,9 @@ __global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const uint4 
         const unsigned q = d & 7u;
         const int j = (d >> 3) & 31, cl = (d >> 8) & 63;
         const unsigned tri = (unsigned)(s_case[s_code[cl * 32 + j]] >> (12 * q)) & 0xfffu;
-        const long long a = edge_rank<LISTED>(rc, cl, j, tri & 15u);
-        const long long b = edge_rank<LISTED>(rc, cl, j, (tri >> 4) & 15u);
-        const long long c = edge_rank<LISTED>(rc, cl, j, tri >> 8);
+        const long long a = id_offset + edge_rank<LISTED>(rc, cl, j, tri & 15u);   // id_offset: slab -> global ids
+        const long long b = id_offset + edge_rank<LISTED>(rc, cl, j, (tri >> 4) & 15u);
+        const long long c = id_offset + edge_rank<LISTED>(rc, cl, j, tri >> 8);
         long long *dst = tris + (size_t)(tile_base + i) * 3;
         st_stream(dst, a); st_stream(dst + 1, b); st_stream(dst + 2, c);
     }

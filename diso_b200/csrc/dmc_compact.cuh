@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
                                                               const uint4 *__restrict__ E, const uint4 *__restrict__ P,
                                                               const unsigned short *__restrict__ C,
                                                               const unsigned *__restrict__ alist, int n_active, T ix, T iy, T iz,
-                                                              const T *__restrict__ adj_dual,
+                                                              const T *__restrict__ adj_dual, long long id_offset,
                                                               long long *__restrict__ quads, T *__restrict__ gedge)
 {
     __shared__ unsigned short s_list[CT_MAX_EDGES];
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
             const unsigned eid = b >> 4;
             const unsigned ord = (s_case[code] >> (2 * eid)) & 3u;
             if (MODE == 0) {
-                id[c] = (long long)(first + ord);
+                id[c] = id_offset + (long long)(first + ord);   // id_offset: slab -> global ids
             } else {
                 const unsigned src = (MODE == 1) ? first + ord : first;
                 const T inv = s_inv[(s_plen[code] >> (4 * ord)) & 7u];

@@ -127,6 +127,71 @@ def cuda_extractor(alg, dtype=torch.float32, grad_mode="reference"):
     return run
 
 
+def _gather_counts(mine, group, world):
+    if world == 1:
+        return mine.cpu()[None]
+    gathered = [torch.zeros_like(mine) for _ in range(world)]
+    if dist.get_backend(group) == "gloo" and mine.is_cuda:
+        cpu = [g.cpu() for g in gathered]
+        dist.all_gather(cpu, mine.cpu(), group=group)
+        return torch.stack(cpu)
+    dist.all_gather(gathered, mine, group=group)
+    return torch.stack(gathered).cpu()
+
+
+def _extract_slab_fused(alg, sdf_own, deform_own, a, b, X, isovalue, normalize, group, rank, world, grad_mode="reference"):
+    """The product path of :func:`extract_slab`: count -> exchange the per-rank totals -> emit with a
+    frame (include/diso_b200.h: diso_b200_frame), so the kernels write global-frame vertices (bit-identical
+    to a single extraction of the whole grid) and global vertex ids directly; what a rank owns are
+    contiguous slices (views) of the emitted arrays.  No elementwise pass touches the outputs."""
+    import diso_b200
+    from diso_b200 import _lib
+    alg_id = {"mc": _lib.ALG_MC, "dmc": _lib.ALG_DMC}[alg]
+    gm = {"reference": _lib.GRAD_REFERENCE, "exact": _lib.GRAD_EXACT}[grad_mode]
+    dev, dt = sdf_own.device, sdf_own.dtype
+    k = 3 if alg == "mc" else 4
+    diso_b200._check_inputs(sdf_own, deform_own, dt)
+    sdf_ext = _HaloExchange.apply(sdf_own, rank, world, group) if world > 1 else sdf_own
+    def_ext = None
+    if deform_own is not None:
+        def_ext = _HaloExchange.apply(deform_own, rank, world, group) if world > 1 else deform_own
+    lo = a - (HALO if rank > 0 else 0)                      # global x of the first local layer
+    A = a + 1 if rank > 0 else 0                            # owned padded layers [A, B), global padded coords
+    B = b + 1 if rank < world - 1 else X + 2
+    lA, lB = A - lo, B - lo
+    with torch.cuda.device(dev):
+        g = sdf_ext.contiguous()
+        d = def_ext.contiguous() if def_ext is not None else None
+        with torch.no_grad():
+            state, counts = diso_b200._count(alg_id, g, isovalue)
+        e0 = e1 = f0 = f1 = 0
+        if counts[_lib.CNT_EDGES] > 0:
+            e_pre, f_pre = diso_b200.layer_prefixes(alg_id, state, tuple(g.shape))
+            e0, e1 = int(e_pre[lA]), int(e_pre[lB])       # crossing edges: MC vertices / DMC quads
+            f0, f1 = int(f_pre[lA]), int(f_pre[lB])       # MC triangles / DMC dual vertices
+        v0, v1, q0, q1 = (e0, e1, f0, f1) if alg == "mc" else (f0, f1, e0, e1)   # owned vertex / face ranges (local ids)
+        # "some value > iso" over the extended slab; the halo layers are other ranks' layers, so the OR over the
+        # ranks is the global test of the reference's early-out (diso/__init__.py:49)
+        mine = torch.tensor([v1 - v0, q1 - q0, counts[_lib.CNT_ANY_GT]], dtype=torch.int64, device=dev)
+        allc = _gather_counts(mine, group, world)
+        v_off = int(allc[:rank, 0].sum())
+        info = dict(vert_offset=v_off, face_offset=int(allc[:rank, 1].sum()), n_verts_total=int(allc[:, 0].sum()),
+                    n_faces_total=int(allc[:, 1].sum()), owned_layers=(A, B))
+        if info["n_verts_total"] == 0 or int(allc[:, 2].sum()) == 0:
+            info.update(n_verts_total=0, n_faces_total=0, vert_offset=0, face_offset=0)
+            return torch.zeros((0, 3), dtype=dt, device=dev), torch.zeros((0, k), dtype=torch.int64, device=dev), info
+        if v1 == v0 and q1 == q0:
+            # nothing owned here, but the neighbours' backward still exchanges halo gradients with this rank:
+            # keep the (empty) result attached to the halo exchange so its backward runs
+            verts = sdf_ext.flatten()[:0].reshape(0, 1).expand(0, 3)
+            if def_ext is not None:
+                verts = verts + def_ext.flatten()[:0].reshape(0, 1)
+            return verts, torch.zeros((0, k), dtype=torch.int64, device=dev), info
+        verts_l, faces_l = diso_b200._Extract.apply(g, d, alg_id, float(isovalue), bool(normalize), gm, state, counts,
+                                                    (lo, X, v_off - v0))
+        return verts_l[v0:v1], faces_l[q0:q1], info
+
+
 def extract_slab(alg, sdf_own, deform_own, x_range, X, isovalue=0.0, normalize=True, group=None, extractor=None):
     """Slab-sharded extraction.  Every rank of `group` calls this with ITS slab
     ``sdf_own = sdf[a:b]`` (and ``deform_own = deform[a:b]`` or None), ``x_range = (a, b)`` from
@@ -141,10 +206,10 @@ def extract_slab(alg, sdf_own, deform_own, x_range, X, isovalue=0.0, normalize=T
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     a, b = x_range
     Y, Z = sdf_own.shape[1], sdf_own.shape[2]
-    if extractor is None:
-        extractor = cuda_extractor(alg, sdf_own.dtype)
     if b - a < HALO and world > 1:
         raise ValueError("slab thinner than the halo")
+    if extractor is None:
+        return _extract_slab_fused(alg, sdf_own, deform_own, a, b, X, isovalue, normalize, group, rank, world)
 
     sdf_ext = _HaloExchange.apply(sdf_own, rank, world, group) if world > 1 else sdf_own
     def_ext = None

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DISO_B200_ABI_VERSION 1
+#define DISO_B200_ABI_VERSION 2
 
 #define DISO_ALG_MC 0
 #define DISO_ALG_DMC 1
@@ -57,6 +57,19 @@ extern "C" {
 #define DISO_CNT_USED 4     /* #used cells (cells whose 8 corners are not all on one side) */
 #define DISO_CNT_EDGE_CHUNKS 5 /* #32-point chunks owning >= 1 crossing edge (the emit kernels visit only those) */
 #define DISO_CNT_CELL_CHUNKS 6 /* #chunks with >= 1 triangle / dual vertex */
+
+/* Frame of a slab inside a larger grid (slab sharding of one grid across GPUs along dim 0,
+ * SURVEY.md section 8e; the reference has no counterpart).  Passed by HOST pointer to emit /
+ * backward; NULL = the grid stands alone.  With a frame, a rank that extracts layers
+ * [x_origin, x_origin + X) of a grid of X_global layers writes vertices in the GLOBAL frame
+ * (bit-identical to a single extraction of the whole grid: the integer x coordinate is offset
+ * before the deformation is added and the normalisation divides by X_global - 1) and face indices
+ * shifted by id_offset (local id -> global id), so no post-processing pass touches the outputs. */
+typedef struct diso_b200_frame {
+    int32_t x_origin;  /* global index of the local grid's first x layer */
+    int32_t X_global;  /* X of the whole grid (<= 0: use the local X) */
+    int64_t id_offset; /* added to every vertex id written to tris / quads (may be negative) */
+} diso_b200_frame;
 
 int diso_b200_abi_version(void);
 
@@ -91,7 +104,7 @@ int diso_b200_count(int alg, const void *sdf, int dtype, int X, int Y, int Z, do
  * proportional to the surface, not the volume).  NULL = visit every chunk. */
 int diso_b200_mc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
                       double iso, const void *state, const int64_t *counts_host, int normalize,
-                      void *verts, int64_t *tris, void *stream);
+                      const diso_b200_frame *frame, void *verts, int64_t *tris, void *stream);
 
 /* Phase 2, dual marching cubes (replaces create_dmc_verts / create_quads,
  * cudualmc.cu:907-955, 1027-1056, and diso/__init__.py:110-116).
@@ -99,7 +112,8 @@ int diso_b200_mc_emit(const void *sdf, const void *deform, int dtype, int X, int
  * scratch: caller-owned, n_quads*3 elements of dtype (edge crossings, each evaluated once). */
 int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
                        double iso, const void *state, const int64_t *counts_host, int normalize,
-                       void *scratch, void *verts, int64_t *quads, void *stream);
+                       const diso_b200_frame *frame, void *scratch, void *verts, int64_t *quads,
+                       void *stream);
 
 /* Backward, marching cubes (replaces adj_create_cell_mc_verts, cumc.cu:474-512, the dense
  * zero-fills of diso/__init__.py:33,40 and the pad-backward slices).  adj_verts is dL/dverts in
@@ -108,14 +122,14 @@ int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, in
  * accumulation is an atomic-free gather in a fixed order, so results are deterministic. */
 int diso_b200_mc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
                           double iso, const void *state, const void *adj_verts, int normalize,
-                          void *adj_sdf, void *adj_deform, void *stream);
+                          const diso_b200_frame *frame, void *adj_sdf, void *adj_deform, void *stream);
 
 /* Backward, dual marching cubes (replaces adj_create_dmc_verts, cudualmc.cu:957-1005).
  * scratch: caller-owned, n_quads*3 elements of dtype (per-edge adjoints). */
 int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
                            double iso, const void *state, const int64_t *counts_host,
-                           const void *adj_verts, int normalize, int grad_mode, void *scratch,
-                           void *adj_sdf, void *adj_deform, void *stream);
+                           const void *adj_verts, int normalize, const diso_b200_frame *frame,
+                           int grad_mode, void *scratch, void *adj_sdf, void *adj_deform, void *stream);
 
 /* Quad -> triangle split of diso/__init__.py:118-147 as three small kernels (no PyTorch
  * temporaries).  verts [n_verts,3] dtype (API frame), quads [n_quads,4] int64, faces

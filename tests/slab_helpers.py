@@ -79,7 +79,7 @@ def worker(rank, world, port, alg, sdf, deform, iso, normalize, use_cuda, out_di
         d_own = deform[a:b].clone().to(dev).requires_grad_(True) if deform is not None else None
         ext = None if use_cuda else oracle_extractor(alg)
         verts, faces, info = parallel.extract_slab(alg, s_own, d_own, (a, b), X, iso, normalize, extractor=ext)
-        if verts.shape[0]:
+        if verts.shape[0] or verts.requires_grad:   # (an empty but attached result keeps the halo backward symmetric)
             i = torch.arange(info["vert_offset"] * 3, (info["vert_offset"] + verts.shape[0]) * 3, dtype=torch.float64).reshape(-1, 3)
             w = torch.cos(i * 0.6180339887 + 0.25).to(verts.dtype).to(dev)
             (verts * w).sum().backward()

@@ -55,13 +55,13 @@ def test_dense_and_listed_tiles_agree(alg, dtype):
         w = torch.cos(torch.arange(nv * 3, dtype=torch.float64).reshape(nv, 3) * 0.618).to(dtype).to(DEV)
         common = (sdf.data_ptr(), deform.data_ptr(), dt, n, n, n, 0.0, state.data_ptr())
         if alg == "mc":
-            _lib.check(L.diso_b200_mc_emit(*common, ch, 1, verts.data_ptr(), faces.data_ptr(), st))
-            _lib.check(L.diso_b200_mc_backward(*common, w.data_ptr(), 1, adj_s.data_ptr(), adj_d.data_ptr(), st))
+            _lib.check(L.diso_b200_mc_emit(*common, ch, 1, None, verts.data_ptr(), faces.data_ptr(), st))
+            _lib.check(L.diso_b200_mc_backward(*common, w.data_ptr(), 1, None, adj_s.data_ptr(), adj_d.data_ptr(), st))
         else:
             scratch = torch.empty((ne, 3), dtype=dtype, device=DEV)
-            _lib.check(L.diso_b200_dmc_emit(*common, ch, 1, scratch.data_ptr(), verts.data_ptr(), faces.data_ptr(), st))
+            _lib.check(L.diso_b200_dmc_emit(*common, ch, 1, None, scratch.data_ptr(), verts.data_ptr(), faces.data_ptr(), st))
             for gm in (_lib.GRAD_REFERENCE, _lib.GRAD_EXACT):
-                _lib.check(L.diso_b200_dmc_backward(*common, ch, w.data_ptr(), 1, gm, scratch.data_ptr(), adj_s.data_ptr(), adj_d.data_ptr(), st))
+                _lib.check(L.diso_b200_dmc_backward(*common, ch, w.data_ptr(), 1, None, gm, scratch.data_ptr(), adj_s.data_ptr(), adj_d.data_ptr(), st))
         torch.cuda.synchronize()
         res.append([t.cpu().numpy() for t in (verts, faces, adj_s, adj_d)])
     for a, b, what in zip(res[0], res[1], ("verts", "faces", "adj_sdf", "adj_deform")):
