@@ -117,7 +117,7 @@ def kernel_bytes(name, G, s, c_mc, c_dmc, deform):
     Vd, Qd = c_dmc["verts"], c_dmc["faces"]
     d3 = 3 if deform else 0
     table = {
-        "sign_pack_f32x4": G * s, "sign_pack": G * s,
+        "sign_pack_f32x4": G * s, "sign_pack_f64x2": G * s, "sign_pack": G * s,
         "classify_scan_mc": 0, "classify_scan_dmc": 0,
         "mc_emit_verts": 3 * Vm * s + d3 * min(Em, G) * s,
         "mc_emit_tris": 3 * Fm * 8,

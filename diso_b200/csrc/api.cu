@@ -51,7 +51,7 @@ int check_dims(int alg, int dtype, int X, int Y, int Z)
     if (X < 1 || Y < 1 || Z < 1) return fail(DISO_E_INVALID, "grid dims must be >= 1 (got %d,%d,%d)", X, Y, Z);
     // 32-bit budget: padded point count and worst-case crossing-edge count must fit in int32/uint32
     const double pts = (double)(X + 2) * (Y + 2) * (Z + 2);
-    if (pts >= 1.4e9) return fail(DISO_E_TOOLARGE, "grid %dx%dx%d exceeds the per-call index budget; shard it into slabs", X, Y, Z);
+    if (pts >= 1.4e9 || Z + 2 >= (1 << 28)) return fail(DISO_E_TOOLARGE, "grid %dx%dx%d exceeds the per-call index budget; shard it into slabs", X, Y, Z);
     return DISO_OK;
 }
 
@@ -194,13 +194,14 @@ int count_impl(int alg, const T *sdf, const Geo &g, double iso, const StateLayou
 
     const T isoT = (T)iso;
     const int warps = 8;
-    const bool vec4 = sizeof(T) == 4 && (g.Z % 4 == 0) && ((reinterpret_cast<uintptr_t>(sdf) & 15) == 0);
-    if (vec4) {
+    constexpr int VN = 16 / (int)sizeof(T);   // values per 128-bit load
+    const bool vec = (g.Z % VN == 0) && ((reinterpret_cast<uintptr_t>(sdf) & 15) == 0);
+    if (vec) {
         const int NA = (g.Z + 31) / 32;
         const size_t smem = (size_t)warps * (NA + 2) * 4;
         const int ctas = std::min(cdiv(g.NR, warps), sm_count() * 6);  // persistent: warps stride over the rows
-        LAUNCH("sign_pack_f32x4", st, sign_pack_f32x4_kernel<<<ctas, warps * 32, smem, st>>>(
-                                          reinterpret_cast<const float *>(sdf), g, (float)isoT, p.S, p.counts));
+        kernel_attrs(reinterpret_cast<const void *>(sign_pack_vec_kernel<T>), "DISO_CARVEOUT_SIGN", -1, smem);
+        LAUNCH(sizeof(T) == 4 ? "sign_pack_f32x4" : "sign_pack_f64x2", st, sign_pack_vec_kernel<T><<<ctas, warps * 32, smem, st>>>(sdf, g, isoT, p.S, p.counts));
     } else {
         LAUNCH("sign_pack", st, sign_pack_kernel<T><<<cdiv(g.NR, warps), warps * 32, 0, st>>>(sdf, g, isoT, p.S, p.counts));
     }

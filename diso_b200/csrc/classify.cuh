@@ -59,18 +59,39 @@ __global__ void __launch_bounds__(256) sign_pack_kernel(const T *__restrict__ sd
     if (__any_sync(FULL, any_gt) && lane == 0) counts[DISO_CNT_ANY_GT] = 1;
 }
 
-// Vectorised K1 for fp32 rows whose length is a multiple of 4 and 16-byte aligned: each lane
-// loads float4s (128-bit), i.e. a warp consumes 512 contiguous bytes per instruction, four
-// instructions per batch.  The grid is persistent (a few CTAs per SM, warps stride over the
+// Vectorised K1 for rows whose length is a multiple of the vector width and 16-byte aligned: each lane
+// loads 128-bit vectors (float4 / double2), i.e. a warp consumes 512 contiguous bytes per instruction,
+// four instructions per batch.  The grid is persistent (a few CTAs per SM, warps stride over the
 // rows) and the loads of the NEXT batch are issued before the current one is digested, so a
 // warp always has 2 KB in flight (the one-row-per-CTA version was bound by CTA turnover: ncu
 // showed 34 % issue activity and 14 % DRAM throughput).
-// The 4-bit nibbles are merged into aligned 32-bit words inside 8-lane groups with three
-// shuffle-OR steps, staged in shared memory, then shifted by the one-point pad offset.
-__global__ void __launch_bounds__(256) sign_pack_f32x4_kernel(const float *__restrict__ sdf, Geo g,
-                                                              float iso, unsigned *__restrict__ S,
-                                                              long long *__restrict__ counts)
+// The per-lane bit groups (4 bits for fp32, 2 for fp64) are merged into aligned 32-bit words inside
+// 8- / 16-lane groups with shuffle-OR steps, staged in shared memory, then shifted by the one-point
+// pad offset.
+template <typename T> struct Vec128;
+template <> struct Vec128<float> {
+    using type = float4;
+    static constexpr int N = 4;
+    static __device__ __forceinline__ float4 fill(float v) { return make_float4(v, v, v, v); }
+    static __device__ __forceinline__ unsigned ge(const float4 &q, float iso) { return (q.x >= iso ? 1u : 0u) | (q.y >= iso ? 2u : 0u) | (q.z >= iso ? 4u : 0u) | (q.w >= iso ? 8u : 0u); }
+    static __device__ __forceinline__ bool gt(const float4 &q, float iso) { return (q.x > iso) | (q.y > iso) | (q.z > iso) | (q.w > iso); }
+};
+template <> struct Vec128<double> {
+    using type = double2;
+    static constexpr int N = 2;
+    static __device__ __forceinline__ double2 fill(double v) { return make_double2(v, v); }
+    static __device__ __forceinline__ unsigned ge(const double2 &q, double iso) { return (q.x >= iso ? 1u : 0u) | (q.y >= iso ? 2u : 0u); }
+    static __device__ __forceinline__ bool gt(const double2 &q, double iso) { return (q.x > iso) | (q.y > iso); }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) sign_pack_vec_kernel(const T *__restrict__ sdf, Geo g, T iso, unsigned *__restrict__ S,
+                                                            long long *__restrict__ counts)
 {
+    using VT = Vec128<T>;
+    using V = typename VT::type;
+    constexpr int N = VT::N;        // values per lane per load
+    constexpr int LPW = 32 / N;     // lanes that share one 32-bit sign word
     extern __shared__ unsigned sm_words[];  // per warp: NA+2 aligned words
     const int lane = threadIdx.x & 31;
     const int wid = threadIdx.x >> 5;
@@ -78,21 +99,21 @@ __global__ void __launch_bounds__(256) sign_pack_f32x4_kernel(const float *__res
     const int nwarps = gridDim.x * warps_per_cta;
     const int NA = (g.Z + 31) / 32;  // aligned words covering z = 0..Z-1
     unsigned *aw = sm_words + wid * (NA + 2);
-    const int nvec = g.Z >> 2;
-    const int nb = (nvec + 127) / 128;  // batches of 4 x 32 float4 per row
+    const int nvec = g.Z / N;
+    const int nb = (nvec + 127) / 128;  // batches of 4 x 32 vectors per row
     bool any_gt = false;
 
-    auto row_ptr = [&](int row) -> const float4 * {
+    auto row_ptr = [&](int row) -> const V * {
         const int xp = row / g.PY, yp = row - xp * g.PY;
         const bool real = xp >= 1 && xp <= g.X && yp >= 1 && yp <= g.Y;
-        return real ? reinterpret_cast<const float4 *>(sdf + ((size_t)(xp - 1) * g.Y + (yp - 1)) * g.Z) : nullptr;
+        return real ? reinterpret_cast<const V *>(sdf + ((size_t)(xp - 1) * g.Y + (yp - 1)) * g.Z) : nullptr;
     };
-    auto load_batch = [&](int row, int b, float4 (&q)[4]) {
-        const float4 *rp = row_ptr(row);
+    auto load_batch = [&](int row, int b, V (&q)[4]) {
+        const V *rp = row_ptr(row);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int v = b * 128 + 32 * u + lane;
-            q[u] = make_float4(iso, iso, iso, iso);  // pad rows / beyond the row: "inside"
+            q[u] = VT::fill(iso);  // pad rows / beyond the row: "inside"
             if (rp && v < nvec) q[u] = __ldcs(rp + v);
         }
     };
@@ -100,7 +121,7 @@ __global__ void __launch_bounds__(256) sign_pack_f32x4_kernel(const float *__res
     // A warp owns whole rows (row = first, first + nwarps, ...) and walks their batches in order,
     // because the aligned words of a row are staged in the warp's private shared-memory slice.
     int row = blockIdx.x * warps_per_cta + wid, b = 0;
-    float4 q[4], qn[4];
+    V q[4], qn[4];
     if (row < g.NR) load_batch(row, 0, q);
     while (row < g.NR) {
         int nrow = row, nbat = b + 1;
@@ -108,14 +129,12 @@ __global__ void __launch_bounds__(256) sign_pack_f32x4_kernel(const float *__res
         if (nrow < g.NR) load_batch(nrow, nbat, qn);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const unsigned nib = (q[u].x >= iso ? 1u : 0u) | (q[u].y >= iso ? 2u : 0u) | (q[u].z >= iso ? 4u : 0u) | (q[u].w >= iso ? 8u : 0u);
-            any_gt |= (q[u].x > iso) | (q[u].y > iso) | (q[u].z > iso) | (q[u].w > iso);
-            unsigned w = nib << (4 * (lane & 7));
-            w |= __shfl_xor_sync(FULL, w, 1);
-            w |= __shfl_xor_sync(FULL, w, 2);
-            w |= __shfl_xor_sync(FULL, w, 4);
-            const int widx = ((b * 128 + 32 * u) >> 3) + (lane >> 3);  // aligned word index: 8 float4 per word
-            if ((lane & 7) == 0 && widx < NA) aw[widx] = w;
+            any_gt |= VT::gt(q[u], iso);
+            unsigned w = VT::ge(q[u], iso) << (N * (lane & (LPW - 1)));
+#pragma unroll
+            for (int d = 1; d < LPW; d <<= 1) w |= __shfl_xor_sync(FULL, w, d);
+            const int widx = (b * 128 + 32 * u) / LPW + lane / LPW;  // aligned word index: LPW vectors per word
+            if ((lane & (LPW - 1)) == 0 && widx < NA) aw[widx] = w;
         }
         if (b == nb - 1) {  // row complete: shift by the pad offset and store
             __syncwarp();

@@ -47,9 +47,9 @@ template <bool LISTED> struct TileRange {
 // chunk in the UNPADDED arrays (may lie outside: validity comes from the flags and the z range).
 struct TilePos {
     int rowbase;     // ((xp-1) Y + (yp-1)) Z + 32 c - 1
-    short xp, yp;
-    int z0;          // 32 c
-    unsigned flags;  // bit0: 1 <= xp <= X   bit1: 1 <= yp <= Y   bit2: xp + 1 <= X   bit3: yp + 1 <= Y
+    int xp, yp;
+    unsigned zf;     // 32 c (28 bits; PZ < 2^28 by the per-call index budget) | flags << 28
+                     // flags bit0: 1 <= xp <= X   bit1: 1 <= yp <= Y   bit2: xp + 1 <= X   bit3: yp + 1 <= Y
 };
 
 __device__ __forceinline__ TilePos make_tile_pos(const Geo &g, int k)
@@ -58,10 +58,10 @@ __device__ __forceinline__ TilePos make_tile_pos(const Geo &g, int k)
     const int xp = r / g.PY, yp = r - xp * g.PY;
     TilePos tp;
     tp.rowbase = ((xp - 1) * g.Y + (yp - 1)) * g.Z + 32 * c - 1;
-    tp.xp = (short)xp; tp.yp = (short)yp;
-    tp.z0 = 32 * c;
-    tp.flags = (unsigned)(xp >= 1 && xp <= g.X) | ((unsigned)(yp >= 1 && yp <= g.Y) << 1) |
-               ((unsigned)(xp + 1 <= g.X) << 2) | ((unsigned)(yp + 1 <= g.Y) << 3);
+    tp.xp = xp; tp.yp = yp;
+    const unsigned flags = (unsigned)(xp >= 1 && xp <= g.X) | ((unsigned)(yp >= 1 && yp <= g.Y) << 1) |
+                           ((unsigned)(xp + 1 <= g.X) << 2) | ((unsigned)(yp + 1 <= g.Y) << 3);
+    tp.zf = (unsigned)(32 * c) | (flags << 28);
     return tp;
 }
 
@@ -166,18 +166,19 @@ __global__ void __launch_bounds__(CT_THREADS) edge_verts_kernel(const T *__restr
         const unsigned d = s_list[i];
         const int axis = d & 3, j = (d >> 2) & 31;
         const TilePos tp = s_pos[(d >> 7) & 63];
-        const int zp = tp.z0 + j, zq = zp + (axis == 2);
+        const unsigned flags = tp.zf >> 28;
+        const int zp = (int)(tp.zf & 0x0fffffffu) + j, zq = zp + (axis == 2);
         const unsigned need1 = axis == 0 ? 6u : (axis == 1 ? 9u : 3u);
-        const bool v0 = (tp.flags & 3u) == 3u && (unsigned)(zp - 1) < (unsigned)g.Z;
-        const bool v1 = (tp.flags & need1) == need1 && (unsigned)(zq - 1) < (unsigned)g.Z;
+        const bool v0 = (flags & 3u) == 3u && (unsigned)(zp - 1) < (unsigned)g.Z;
+        const bool v1 = (flags & need1) == need1 && (unsigned)(zq - 1) < (unsigned)g.Z;
         const int i0 = tp.rowbase + j;
         const int i1 = i0 + (axis == 0 ? sYZ : (axis == 1 ? sZ : 1));
         const T d0 = v0 ? __ldg(sdf + i0) : padv;
         const T d1 = v1 ? __ldg(sdf + i1) : padv;
         const T t = edge_t(d0, d1, iso);
-        const int xg = (int)tp.xp + epi.x0;
-        Vec3<T> p0{T(xg), T((int)tp.yp), T(zp)};
-        Vec3<T> p1{T(xg + (axis == 0)), T((int)tp.yp + (axis == 1)), T(zq)};
+        const int xg = tp.xp + epi.x0;
+        Vec3<T> p0{T(xg), T(tp.yp), T(zp)};
+        Vec3<T> p1{T(xg + (axis == 0)), T(tp.yp + (axis == 1)), T(zq)};
         if (has_def) {
             // the pad layer carries zero deformation (diso/__init__.py:54)
             if (v0) {

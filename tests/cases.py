@@ -34,6 +34,8 @@ CASES = {
     "longrow_3x4x644": (lambda: syn.random_sdf((3, 4, 644), "dense", 13), True, 0.0),   # > 512 values per row: 2 load batches
     "longrow_2x3x1100": (lambda: syn.random_sdf((2, 3, 1100), "flexi", 14), False, 0.0),  # 3 batches, NC > 32
     "longrow_1x2x1101": (lambda: syn.random_sdf((1, 2, 1101), "dense", 15), True, 0.0),  # scalar sign pass, NC > 32
+    "tall_1x530000x2": (lambda: syn.random_sdf((1, 530000, 2), "flexi", 16), True, 0.0),   # > 65535 backward tiles in y: flat-grid fallback
+    "deep_40000x2x3": (lambda: syn.random_sdf((40000, 2, 3), "dense", 17), True, 0.0),     # coordinates beyond 16 bits in x
     "tiny_1x1x1": (lambda: torch.full((1, 1, 1), -0.3), True, 0.0),
     "tiny_2x2x2": (lambda: syn.random_sdf(2, "dense", 6), True, 0.0),
     "thin_1x7x33": (lambda: syn.random_sdf((1, 7, 33), "dense", 7), True, 0.0),
