@@ -195,6 +195,31 @@ __device__ __forceinline__ unsigned cell_code(const CellWords &w, int j)
     return c;
 }
 
+// Case indices of all 32 cells of a chunk at once: the 8 (corner) x 32 (cell) bit matrix is transposed in
+// four 8x8 blocks (three masked swap rounds each).  codes[i] holds cells 4i .. 4i+3, one byte per cell.
+// ~110 instructions per chunk instead of ~23 per used cell for the bit-by-bit gather of cell_code().
+template <int ALG>
+__device__ __forceinline__ void cell_codes32(const CellWords &w, unsigned (&codes)[8])
+{
+    unsigned W[8];
+    W[0] = w.A; W[1] = w.B; W[4] = w.A1; W[5] = w.B1;
+    if (ALG == DISO_ALG_MC) { W[2] = w.C; W[3] = w.D; W[6] = w.C1; W[7] = w.D1; }
+    else                    { W[2] = w.D; W[3] = w.C; W[6] = w.D1; W[7] = w.C1; }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const unsigned sel = (unsigned)g | ((unsigned)(4 + g) << 4);   // byte g of the first, byte g of the second operand
+        const unsigned lo = __byte_perm(__byte_perm(W[0], W[1], sel), __byte_perm(W[2], W[3], sel), 0x5410);
+        const unsigned hi = __byte_perm(__byte_perm(W[4], W[5], sel), __byte_perm(W[6], W[7], sel), 0x5410);
+        unsigned long long x = ((unsigned long long)hi << 32) | lo;   // row i (byte i) = corner i, bit c = cell 8g + c
+        unsigned long long t;
+        t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull;  x = x ^ t ^ (t << 7);
+        t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull; x = x ^ t ^ (t << 14);
+        t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull; x = x ^ t ^ (t << 28);
+        codes[2 * g] = (unsigned)x;                                    // byte c = case index of cell 8g + c
+        codes[2 * g + 1] = (unsigned)(x >> 32);
+    }
+}
+
 // DMC case index of the cell at (chunk k, bit j) computed from scratch (used for the
 // ambiguity test's neighbour, cudualmc.cu:828-829).  j may be -1 or 32 (previous/next chunk).
 __device__ __forceinline__ unsigned dmc_code_at(const unsigned *__restrict__ S, const Geo &g, int k, int j)
@@ -261,51 +286,98 @@ __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const u
 
     unsigned mx = 0, my = 0, mz = 0, lo = 0, hi = 0, used = 0;
     unsigned na = 0, nb = 0, nused = 0;
+    CellWords w{FULL, FULL, FULL, FULL, FULL, FULL, FULL, FULL};
     if (k < g.NCH) {
-        CellWords w = load_cell_words(S, g, k);
+        w = load_cell_words(S, g, k);
         mx = w.A ^ w.B;
         my = w.A ^ w.D;
         mz = w.A ^ w.A1;
         na = __popc(mx) + __popc(my) + __popc(mz);
         used = used_mask(w);
         nused = __popc(used);
+    }
+    // Dense warps (many used cells per chunk: random fields) take the transposed, fully predicated path
+    // below: all 32 cells in straight-line code, no per-lane loop trip counts to diverge on.  Warps that
+    // only graze a smooth surface keep the short per-cell loops.
+    const bool dense_warp = __reduce_max_sync(FULL, nused) > 8u;
+    {
         if (used) {
             int r = k / g.NC, c = k - r * g.NC;
             int xp = r / g.PY, yp = r - xp * g.PY;
             unsigned short *crow = reinterpret_cast<unsigned short *>(s_cw + tid * CW_STRIDE);
             if (ALG == DISO_ALG_MC) {
-                unsigned u = used;
-                while (u) {  // ascending j: nb is the cell's offset inside the chunk
-                    const int j = __ffs(u) - 1;
-                    u &= u - 1;
-                    const unsigned code = cell_code<ALG>(w, j);
-                    crow[j] = (unsigned short)(code | (nb << 8));
-                    nb += s_tab[code];
+                if (dense_warp) {
+                    unsigned codes[8];
+                    cell_codes32<ALG>(w, codes);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {   // ascending j: nb is the cell's offset inside the chunk
+                        if ((used >> j) & 1u) {
+                            const unsigned code = (codes[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                            crow[j] = (unsigned short)(code | (nb << 8));
+                            nb += s_tab[code];
+                        }
+                    }
+                } else {
+                    unsigned u = used;
+                    while (u) {
+                        const int j = __ffs(u) - 1;
+                        u &= u - 1;
+                        const unsigned code = cell_code<ALG>(w, j);
+                        crow[j] = (unsigned short)(code | (nb << 8));
+                        nb += s_tab[code];
+                    }
                 }
             } else {
                 // Three passes keep the warp converged: only ~13 % of the used cells of a random field
                 // are "problematic", but inside one per-cell loop nearly every warp iteration would
                 // have SOME lane on the long neighbour-lookup path.
                 unsigned prob = 0;
-                for (unsigned u = used; u; u &= u - 1) {           // 1: raw case index, who needs the test
-                    const int j = __ffs(u) - 1;
-                    const unsigned code = cell_code<ALG>(w, j);
-                    crow[j] = (unsigned short)code;
-                    prob |= (s_tab[code] >> 31) << j;
+                if (dense_warp) {                                      // 1: raw case index, who needs the test
+                    unsigned codes[8];
+                    cell_codes32<ALG>(w, codes);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if ((used >> j) & 1u) {
+                            const unsigned code = (codes[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                            crow[j] = (unsigned short)code;
+                            prob |= (s_tab[code] >> 31) << j;
+                        }
+                    }
+                } else {
+                    for (unsigned u = used; u; u &= u - 1) {
+                        const int j = __ffs(u) - 1;
+                        const unsigned code = cell_code<ALG>(w, j);
+                        crow[j] = (unsigned short)code;
+                        prob |= (s_tab[code] >> 31) << j;
+                    }
                 }
                 for (unsigned u = prob; u; u &= u - 1) {           // 2: ambiguity test (cudualmc.cu:815-839)
                     const int j = __ffs(u) - 1;
                     const unsigned code = crow[j];
                     if (dmc_flip(S, g, s_tab, k, xp, yp, c, j, code)) crow[j] = (unsigned short)(code ^ 0xffu);
                 }
-                for (unsigned u = used; u; u &= u - 1) {           // 3: patch counts + offsets, ascending j
-                    const int j = __ffs(u) - 1;
-                    const unsigned code = crow[j];
-                    crow[j] = (unsigned short)(code | (nb << 8));
-                    const unsigned np = (s_tab[code] >> 24) & 7u;  // 1..4
-                    nb += np;
-                    lo |= ((np - 1u) & 1u) << j;
-                    hi |= ((np - 1u) >> 1) << j;
+                if (dense_warp) {                                      // 3: patch counts + offsets, ascending j
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if ((used >> j) & 1u) {
+                            const unsigned code = crow[j];
+                            crow[j] = (unsigned short)(code | (nb << 8));
+                            const unsigned np = (s_tab[code] >> 24) & 7u;  // 1..4
+                            nb += np;
+                            lo |= ((np - 1u) & 1u) << j;
+                            hi |= ((np - 1u) >> 1) << j;
+                        }
+                    }
+                } else {
+                    for (unsigned u = used; u; u &= u - 1) {
+                        const int j = __ffs(u) - 1;
+                        const unsigned code = crow[j];
+                        crow[j] = (unsigned short)(code | (nb << 8));
+                        const unsigned np = (s_tab[code] >> 24) & 7u;  // 1..4
+                        nb += np;
+                        lo |= ((np - 1u) & 1u) << j;
+                        hi |= ((np - 1u) >> 1) << j;
+                    }
                 }
             }
         }

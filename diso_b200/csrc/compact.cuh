@@ -319,9 +319,10 @@ __global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const uint4 
         const unsigned q = d & 7u;
         const int j = (d >> 3) & 31, cl = (d >> 8) & 63;
         const unsigned tri = (unsigned)(s_case[s_code[cl * 32 + j]] >> (12 * q)) & 0xfffu;
-        const long long a = id_offset + edge_rank<LISTED>(rc, cl, j, tri & 15u);   // id_offset: slab -> global ids
-        const long long b = id_offset + edge_rank<LISTED>(rc, cl, j, (tri >> 4) & 15u);
-        const long long c = id_offset + edge_rank<LISTED>(rc, cl, j, tri >> 8);
+        long long a = edge_rank<LISTED>(rc, cl, j, tri & 15u);
+        long long b = edge_rank<LISTED>(rc, cl, j, (tri >> 4) & 15u);
+        long long c = edge_rank<LISTED>(rc, cl, j, tri >> 8);
+        if (id_offset != 0) { a += id_offset; b += id_offset; c += id_offset; }   // slab -> global ids (uniform branch)
         long long *dst = tris + (size_t)(tile_base + i) * 3;
         st_stream(dst, a); st_stream(dst + 1, b); st_stream(dst + 2, c);
     }

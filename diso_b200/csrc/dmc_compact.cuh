@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
             const unsigned eid = b >> 4;
             const unsigned ord = (s_case[code] >> (2 * eid)) & 3u;
             if (MODE == 0) {
-                id[c] = id_offset + (long long)(first + ord);   // id_offset: slab -> global ids
+                id[c] = (long long)(first + ord);
             } else {
                 const unsigned src = (MODE == 1) ? first + ord : first;
                 const T inv = s_inv[(s_plen[code] >> (4 * ord)) & 7u];
@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
         }
         const size_t rank = (size_t)tile_base + i;
         if (MODE == 0) {
+            if (id_offset != 0) { id[0] += id_offset; id[1] += id_offset; id[2] += id_offset; id[3] += id_offset; }   // slab -> global ids
             longlong2 *dst = reinterpret_cast<longlong2 *>(quads + rank * 4);
             __stcs(dst, make_longlong2(id[0], id[1]));
             __stcs(dst + 1, make_longlong2(id[2], id[3]));
