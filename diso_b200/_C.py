@@ -80,6 +80,7 @@ class _Base:
             p = lambda t: None if t is None else t.data_ptr()
             if self._alg == _lib.ALG_MC:
                 _lib.check(L.diso_b200_mc_backward(grid.data_ptr(), p(deform), dt, X, Y, Z, float(iso), state.data_ptr(),
+                                                   ctypes.cast(counts_c, ctypes.c_void_p),
                                                    adj_verts.data_ptr(), 0, None, g_grid.data_ptr(), p(g_def), st))
             else:
                 scratch = torch.empty((max(nf, 1), 3), dtype=self._dtype, device=grid.device)

@@ -114,7 +114,8 @@ class _Extract(Function):
             dt = _DTYPES[grid.dtype]
             if ctx.alg == _lib.ALG_MC:
                 _lib.check(L.diso_b200_mc_backward(grid.data_ptr(), _ptr(deform), dt, X, Y, Z, ctx.isovalue,
-                                                   state.data_ptr(), adj_verts.data_ptr(), int(ctx.normalize),
+                                                   state.data_ptr(), ctypes.cast(ctx.counts, ctypes.c_void_p),
+                                                   adj_verts.data_ptr(), int(ctx.normalize),
                                                    _lib.frame_ptr(ctx.frame), adj_grid.data_ptr(), _ptr(adj_deform), _stream()))
             else:
                 scratch = torch.empty((max(ctx.n_edges, 1), 3), dtype=grid.dtype, device=grid.device)

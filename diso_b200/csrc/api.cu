@@ -64,6 +64,7 @@ struct StatePtrs {
     void *aux;
     unsigned short *C;
     unsigned *active;     // [0, NCH): chunks owning crossing edges, [NCH, 2 NCH): chunks with faces (ascending)
+    unsigned *bwd;        // work area of the sparse backward
 };
 
 StatePtrs state_ptrs(void *state, const StateLayout &L)
@@ -78,6 +79,7 @@ StatePtrs state_ptrs(void *state, const StateLayout &L)
     p.aux = b + L.off_aux;
     p.C = reinterpret_cast<unsigned short *>(b + L.off_cell);
     p.active = reinterpret_cast<unsigned *>(b + L.off_active);
+    p.bwd = reinterpret_cast<unsigned *>(b + L.off_bwd);
     return p;
 }
 
@@ -227,8 +229,10 @@ int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const 
     }
     if (tc.ctas) {
         const uint2 *F = reinterpret_cast<const uint2 *>(p.aux);
-        if (tc.list) LAUNCH("mc_emit_tris", st, mc_tris_kernel<true><<<tc.ctas, CT_THREADS, 0, st>>>(g, p.E, F, p.C, tc.list, tc.n_active, fr.id_offset, tris));
-        else LAUNCH("mc_emit_tris", st, mc_tris_kernel<false><<<tc.ctas, CT_THREADS, 0, st>>>(g, p.E, F, p.C, tc.list, tc.n_active, fr.id_offset, tris));
+#define DISO_TRIS(LISTED, OFFSET) LAUNCH("mc_emit_tris", st, (mc_tris_kernel<LISTED, OFFSET><<<tc.ctas, CT_THREADS, 0, st>>>(g, p.E, F, p.C, tc.list, tc.n_active, fr.id_offset, tris)))
+        if (fr.id_offset != 0) { if (tc.list) DISO_TRIS(true, true); else DISO_TRIS(false, true); }
+        else                   { if (tc.list) DISO_TRIS(true, false); else DISO_TRIS(false, false); }
+#undef DISO_TRIS
     }
     return DISO_OK;
 }
@@ -256,61 +260,66 @@ int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const
         else LAUNCH("dmc_emit_verts", st, (dmc_dual_verts_kernel<T, false><<<tc.ctas, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, tc.list, tc.n_active, verts)));
     }
     if (te.ctas) {
-        if (te.list) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, true><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, fr.id_offset, quads, nullptr)));
-        else LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, false><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, fr.id_offset, quads, nullptr)));
+#define DISO_QUADS(LISTED, OFFSET) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, LISTED, OFFSET><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, fr.id_offset, quads, nullptr)))
+        if (fr.id_offset != 0) { if (te.list) DISO_QUADS(true, true); else DISO_QUADS(false, true); }
+        else                   { if (te.list) DISO_QUADS(true, false); else DISO_QUADS(false, false); }
+#undef DISO_QUADS
     }
     return DISO_OK;
 }
 
 template <typename T, bool HAS_DEF, int BX, int BY>
 int launch_bwd_compact(const T *sdf, const T *deform, const Geo &g, T isoT, T padv, T ix, T iy, T iz, const uint4 *E,
-                       const T *gsrc, T *adj_sdf, T *adj_deform, cudaStream_t st)
+                       const T *gsrc, T *adj_sdf, T *adj_deform, unsigned *work, bool sparse, cudaStream_t st)
 {
-    auto kern = mc_backward_compact_kernel<T, HAS_DEF, BX, BY>;
     static const int smem_pad = env_int("DISO_BWD_SMEM_PAD", 0);   // experiment knob: caps the CTAs per SM
     const size_t smem = bwd_compact_smem<T, HAS_DEF, BX, BY>() + (size_t)smem_pad;
+    const int ntx = cdiv(g.X, BX), nty = cdiv(g.Y, BY);
+    const long long nblk = (long long)ntx * nty * g.NC;
     // L1 capacity matters more than occupancy here (the gathers of sdf / deform / adjoints hit L1 ~63 %): with the
     // driver's default carve-out (8 CTAs/SM, ~28 KB L1) the fp32 kernel takes 2.48 ms at 512^3, with 132 KB of
     // shared memory (5 CTAs, ~124 KB L1) 1.72 ms; fp64: 3.18 ms at 72 % vs 4.59 ms at 100 % (sweeps in DESIGN.md)
-    kernel_attrs(reinterpret_cast<const void *>(kern), "DISO_CARVEOUT_BWD", sizeof(T) == 4 ? 58 : 72, smem);
-    const int ntx = cdiv(g.X, BX), nty = cdiv(g.Y, BY);
+    const int carve = sizeof(T) == 4 ? 58 : 72;
+    if (sparse) {
+        // zero fill + list of the touched blocks + persistent grid over that list (mc_backward_compact.cuh)
+        auto kern = mc_backward_queue_kernel<T, HAS_DEF, BX, BY>;
+        kernel_attrs(reinterpret_cast<const void *>(kern), "DISO_CARVEOUT_BWD", carve, smem);
+        const size_t G = (size_t)g.X * g.Y * g.Z;
+        CU_TRY(cudaMemsetAsync(adj_sdf, 0, G * sizeof(T), st));
+        if (HAS_DEF) CU_TRY(cudaMemsetAsync(adj_deform, 0, G * 3 * sizeof(T), st));
+        CU_TRY(cudaMemsetAsync(work, 0, 64, st));
+        LAUNCH("mc_backward_mark", st, (bwd_mark_kernel<BX, BY><<<cdiv(nblk, 256), 256, 0, st>>>(g, E, ntx, nty, work)));
+        const int ctas = (int)std::min<long long>(nblk, (long long)sm_count() * 6);
+        LAUNCH("mc_backward", st, kern<<<ctas, BC_THREADS, smem, st>>>(sdf, deform, g, isoT, padv, ix, iy, iz, E, gsrc, adj_sdf, adj_deform, nty, work));
+        return DISO_OK;
+    }
+    auto kern = mc_backward_compact_kernel<T, HAS_DEF, BX, BY>;
+    kernel_attrs(reinterpret_cast<const void *>(kern), "DISO_CARVEOUT_BWD", carve, smem);
     // 3-D grid (chunk, y tile, x tile): no index divisions in the kernel; shapes whose tile counts exceed
     // the 65535 limit of grid.y / grid.z fall back to a flat grid decoded with divisions
     const bool flat = nty > 65535 || ntx > 65535;
-    const dim3 grid = flat ? dim3((unsigned)((long long)ntx * nty * g.NC), 1, 1) : dim3((unsigned)g.NC, (unsigned)nty, (unsigned)ntx);
+    const dim3 grid = flat ? dim3((unsigned)nblk, 1, 1) : dim3((unsigned)g.NC, (unsigned)nty, (unsigned)ntx);
     LAUNCH("mc_backward", st, kern<<<grid, BC_THREADS, smem, st>>>(sdf, deform, g, isoT, padv, ix, iy, iz, E, gsrc, adj_sdf,
                                                                  adj_deform, ntx, nty, flat ? 1 : 0));
     return DISO_OK;
 }
 
 template <typename T>
-int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const T *adj_verts,
-                     int normalize, int X_global, T *adj_sdf, T *adj_deform, cudaStream_t st)
+int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const int64_t *counts_host,
+                     const T *adj_verts, int normalize, int X_global, T *adj_sdf, T *adj_deform, cudaStream_t st)
 {
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     // chain rule of verts / (dims - 1): multiply by the reciprocal (gradients carry a 1e-5 bar, not bit parity)
     const T ix = normalize ? T(1) / (T(X_global) - T(1)) : T(1), iy = normalize ? T(1) / (T(g.Y) - T(1)) : T(1),
             iz = normalize ? T(1) / (T(g.Z) - T(1)) : T(1);
-    // block shape from a sweep on B200 (512^3 rand-flexi): 4x8 1.90 ms, 8x4 1.94, 8x8 2.05, 4x4 2.21
-#ifdef DISO_TUNE
-    if (deform && sizeof(T) == 4) {
-        static const int tile = env_int("DISO_BWD_TILE", 0);
-#define DISO_BT(BX, BY) return launch_bwd_compact<T, true, BX, BY>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, adj_verts, adj_sdf, adj_deform, st)
-        switch (tile) {
-        case 1: DISO_BT(4, 4);
-        case 2: DISO_BT(2, 8);
-        case 3: DISO_BT(8, 4);
-        case 4: DISO_BT(2, 16);
-        case 5: DISO_BT(6, 8);
-        case 6: DISO_BT(3, 8);
-        case 7: DISO_BT(4, 6);
-        default: break;
-        }
-#undef DISO_BT
-    }
-#endif
-    if (deform) return launch_bwd_compact<T, true, 4, 8>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, adj_verts, adj_sdf, adj_deform, st);
-    return launch_bwd_compact<T, false, 4, 8>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, adj_verts, adj_sdf, adj_deform, st);
+    // sparse surface (known from the counts the caller read back in the forward): fewer than 1/8 of the chunks own a
+    // crossing edge -> zero fill + touched-block list instead of one CTA per block
+    static const int force = env_int("DISO_BWD_SPARSE", -1);   // experiment knob: 0 / 1 force the path
+    bool sparse = counts_host && counts_host[DISO_CNT_EDGE_CHUNKS] * 8 < (long long)g.NCH;
+    if (force >= 0) sparse = force != 0;
+    // block shape from a sweep on B200 (512^3 rand-flexi): 4x8 1.72 ms, 3x8 / 4x6 1.69, 8x4 1.76, 6x8 1.82, 4x4 1.92
+    if (deform) return launch_bwd_compact<T, true, BWD_BX, BWD_BY>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, adj_verts, adj_sdf, adj_deform, p.bwd, sparse, st);
+    return launch_bwd_compact<T, false, BWD_BX, BWD_BY>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, adj_verts, adj_sdf, adj_deform, p.bwd, sparse, st);
 }
 
 template <typename T>
@@ -327,7 +336,7 @@ int dmc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, c
         else                              { if (te.list) DISO_ADJ(2, true) else DISO_ADJ(2, false) }
 #undef DISO_ADJ
     }
-    return mc_backward_impl<T>(sdf, deform, g, iso, p, scratch, 0, g.X, adj_sdf, adj_deform, st);
+    return mc_backward_impl<T>(sdf, deform, g, iso, p, counts_host, scratch, 0, g.X, adj_sdf, adj_deform, st);
 }
 
 }  // namespace
@@ -443,8 +452,8 @@ int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, in
 }
 
 int diso_b200_mc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
-                          const void *state, const void *adj_verts, int normalize, const diso_b200_frame *frame,
-                          void *adj_sdf, void *adj_deform, void *stream)
+                          void *state, const int64_t *counts_host, const void *adj_verts, int normalize,
+                          const diso_b200_frame *frame, void *adj_sdf, void *adj_deform, void *stream)
 {
     int rc = check_dims(DISO_ALG_MC, dtype, X, Y, Z);
     if (rc) return rc;
@@ -452,19 +461,19 @@ int diso_b200_mc_backward(const void *sdf, const void *deform, int dtype, int X,
     if ((deform == nullptr) != (adj_deform == nullptr)) return fail(DISO_E_INVALID, "deform and adj_deform must both be given or both be NULL");
     const Geo g = make_geo(X, Y, Z);
     const Frame fr = make_frame(frame, X);
-    const StatePtrs p = state_ptrs(const_cast<void *>(state), make_layout(DISO_ALG_MC, g));
+    const StatePtrs p = state_ptrs(state, make_layout(DISO_ALG_MC, g));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == DISO_F32)
-        return mc_backward_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p,
+        return mc_backward_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, counts_host,
                                        static_cast<const float *>(adj_verts), normalize, fr.X_global, static_cast<float *>(adj_sdf),
                                        static_cast<float *>(adj_deform), st);
-    return mc_backward_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p,
+    return mc_backward_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, counts_host,
                                     static_cast<const double *>(adj_verts), normalize, fr.X_global, static_cast<double *>(adj_sdf),
                                     static_cast<double *>(adj_deform), st);
 }
 
 int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
-                           const void *state, const int64_t *counts_host, const void *adj_verts, int normalize,
+                           void *state, const int64_t *counts_host, const void *adj_verts, int normalize,
                            const diso_b200_frame *frame, int grad_mode, void *scratch, void *adj_sdf, void *adj_deform,
                            void *stream)
 {
@@ -475,7 +484,7 @@ int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X
     if (grad_mode != DISO_GRAD_REFERENCE && grad_mode != DISO_GRAD_EXACT) return fail(DISO_E_INVALID, "unknown grad_mode %d", grad_mode);
     const Geo g = make_geo(X, Y, Z);
     const Frame fr = make_frame(frame, X);
-    const StatePtrs p = state_ptrs(const_cast<void *>(state), make_layout(DISO_ALG_DMC, g));
+    const StatePtrs p = state_ptrs(state, make_layout(DISO_ALG_DMC, g));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == DISO_F32)
         return dmc_backward_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, counts_host,

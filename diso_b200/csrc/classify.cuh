@@ -271,8 +271,12 @@ __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const u
     // words keeps the per-thread 2-byte writes of one warp in 32 distinct banks
     constexpr int CW_STRIDE = 17;
     __shared__ unsigned s_cw[SCAN_TILE * CW_STRIDE];
+    __shared__ unsigned s_any_cells;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < CW_STRIDE; ++i) s_cw[i * SCAN_TILE + tid] = 0u;
+    if (tid == 0) s_any_cells = 0u;
     if (ALG == DISO_ALG_MC) s_tab[tid] = (unsigned)(T_MC_CASE[tid] >> 60);
     else                    s_tab[tid] = T_DMC_CASE[tid];
     if (tid == 0) { s_tile = atomicAdd(ticket, 1u); s_used_tot = 0; }
@@ -296,12 +300,8 @@ __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const u
     // below: all 32 cells in straight-line code, no per-lane loop trip counts to diverge on.  Warps that
     // only graze a smooth surface keep the short per-cell loops.
     const bool dense_warp = __reduce_max_sync(FULL, nused) > 8u;
-    // tiles without a used cell (most of the volume around a smooth surface) neither stage nor flush per-cell words
-    const bool any_cells = __syncthreads_or(nused != 0u) != 0;
-    if (any_cells) {
-#pragma unroll
-        for (int i = 0; i < CW_STRIDE; ++i) s_cw[i * SCAN_TILE + tid] = 0u;
-        __syncthreads();
+    if (__any_sync(FULL, nused != 0u) && lane == 0) s_any_cells = 1u;
+    {
         if (used) {
             int r = k / g.NC, c = k - r * g.NC;
             int xp = r / g.PY, yp = r - xp * g.PY;
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(SCAN_TILE) classify_scan_kernel(Geo g, const u
 
     // flush the staged per-cell words: 16 words (32 cells) per chunk, coalesced; a scan tile without
     // used cells is skipped (its words are never read), so sparse surfaces write almost nothing
-    if (any_cells) {
+    if (s_any_cells) {
         unsigned *cout = reinterpret_cast<unsigned *>(C) + (size_t)tile * SCAN_TILE * 16;
         const int rows = min(SCAN_TILE, g.NCH - tile * SCAN_TILE);
         for (int i = tid; i < rows * 16; i += SCAN_TILE) cout[i] = s_cw[(i >> 4) * CW_STRIDE + (i & 15)];

@@ -66,6 +66,7 @@ struct __align__(64) TileDesc {
 };
 
 constexpr int SCAN_TILE = 256;  // chunks per scan tile == threads per classify CTA
+constexpr int BWD_BX = 4, BWD_BY = 8;  // rows per backward block (x, y); one 32-point chunk in z
 
 // Byte offsets of the arrays inside the caller-owned state buffer.
 struct StateLayout {
@@ -78,6 +79,7 @@ struct StateLayout {
     size_t off_cell;     // u16 C[(NCH + 8) * 32] per-cell {case index | offset of first triangle / dual vertex << 8}
     size_t off_active;   // u32 active-chunk lists (ascending chunk id): [0, NCH) chunks owning crossing
                          // edges, [NCH, 2 NCH) chunks with faces
+    size_t off_bwd;      // u32 work area of the sparse backward: {count, cursor, pad[14]} + ids of the touched blocks
     size_t total;
     int n_tiles;
     int sign_tail;
@@ -110,6 +112,9 @@ inline StateLayout make_layout(int alg, const Geo &g)
     o = align_up(o, 256);
     L.off_active = o;
     o += (size_t)g.NCH * 2 * 4;
+    o = align_up(o, 256);
+    L.off_bwd = o;
+    o += ((size_t)((g.X + BWD_BX - 1) / BWD_BX) * ((g.Y + BWD_BY - 1) / BWD_BY) * g.NC + 16) * 4;
     L.total = align_up(o, 256);
     return L;
 }

@@ -260,7 +260,9 @@ __device__ __forceinline__ unsigned edge_rank(const RecCache<LISTED> &rc, int cl
 // ------------------------------------------------------------------------------------------
 constexpr int CT_MAX_TRIS = CT_CHUNKS * 160;
 
-template <bool LISTED>
+// OFFSET: add id_offset to every index (slab -> global ids); a separate instantiation keeps the 64-bit adds
+// out of the standalone kernel (they cost 2.5 % there).
+template <bool LISTED, bool OFFSET>
 __global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const uint4 *__restrict__ E, const uint2 *__restrict__ F,
                                                            const unsigned short *__restrict__ C,
                                                            const unsigned *__restrict__ alist, int n_active,
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const uint4 
         long long a = edge_rank<LISTED>(rc, cl, j, tri & 15u);
         long long b = edge_rank<LISTED>(rc, cl, j, (tri >> 4) & 15u);
         long long c = edge_rank<LISTED>(rc, cl, j, tri >> 8);
-        if (id_offset != 0) { a += id_offset; b += id_offset; c += id_offset; }   // slab -> global ids (uniform branch)
+        if (OFFSET) { a += id_offset; b += id_offset; c += id_offset; }
         long long *dst = tris + (size_t)(tile_base + i) * 3;
         st_stream(dst, a); st_stream(dst + 1, b); st_stream(dst + 2, c);
     }

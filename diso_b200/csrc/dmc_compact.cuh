@@ -16,7 +16,8 @@ namespace diso {
 
 // MODE 0: quads.  MODE 1: exact adjoint.  MODE 2: reference-compatible adjoint (every patch of a
 // cell reads the adjoint of the cell's FIRST dual vertex, cudualmc.cu:975,990).
-template <typename T, int MODE, bool LISTED>
+// OFFSET (MODE 0 only): add id_offset to every index (slab -> global ids).
+template <typename T, int MODE, bool LISTED, bool OFFSET = false>
 __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const unsigned *__restrict__ S,
                                                               const uint4 *__restrict__ E, const uint4 *__restrict__ P,
                                                               const unsigned short *__restrict__ C,
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
         }
         const size_t rank = (size_t)tile_base + i;
         if (MODE == 0) {
-            if (id_offset != 0) { id[0] += id_offset; id[1] += id_offset; id[2] += id_offset; id[3] += id_offset; }   // slab -> global ids
+            if (OFFSET) { id[0] += id_offset; id[1] += id_offset; id[2] += id_offset; id[3] += id_offset; }
             longlong2 *dst = reinterpret_cast<longlong2 *>(quads + rank * 4);
             __stcs(dst, make_longlong2(id[0], id[1]));
             __stcs(dst + 1, make_longlong2(id[2], id[3]));

@@ -119,15 +119,19 @@ int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, in
  * zero-fills of diso/__init__.py:33,40 and the pad-backward slices).  adj_verts is dL/dverts in
  * the API frame (after -1 / normalisation), [n_verts,3] contiguous.  adj_sdf [X,Y,Z] and
  * adj_deform [X,Y,Z,3] (NULL iff deform is NULL) are FULLY written (zeros included);
- * accumulation is an atomic-free gather in a fixed order, so results are deterministic. */
+ * accumulation is an atomic-free gather in a fixed order, so results are deterministic.
+ * counts_host: as for emit (NULL allowed); on sparse surfaces it selects the zero-fill + touched-block
+ * path, which uses a small work area inside `state` (hence not const: do not run two backward
+ * passes on the SAME state concurrently on different streams). */
 int diso_b200_mc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
-                          double iso, const void *state, const void *adj_verts, int normalize,
-                          const diso_b200_frame *frame, void *adj_sdf, void *adj_deform, void *stream);
+                          double iso, void *state, const int64_t *counts_host, const void *adj_verts,
+                          int normalize, const diso_b200_frame *frame, void *adj_sdf, void *adj_deform,
+                          void *stream);
 
 /* Backward, dual marching cubes (replaces adj_create_dmc_verts, cudualmc.cu:957-1005).
  * scratch: caller-owned, n_quads*3 elements of dtype (per-edge adjoints). */
 int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
-                           double iso, const void *state, const int64_t *counts_host,
+                           double iso, void *state, const int64_t *counts_host,
                            const void *adj_verts, int normalize, const diso_b200_frame *frame,
                            int grad_mode, void *scratch, void *adj_sdf, void *adj_deform, void *stream);
 

@@ -71,6 +71,6 @@ def test_argument_errors_return_codes(lib):
     assert rc == -2  # state too small
     rc = lib.diso_b200_count(0, ctypes.c_void_p(256), 0, 2000, 2000, 2000, 0.0, ctypes.c_void_p(256), 1 << 40, None)
     assert rc == -4  # too large for one call
-    rc = lib.diso_b200_mc_backward(ctypes.c_void_p(256), ctypes.c_void_p(256), 0, 4, 4, 4, 0.0, ctypes.c_void_p(256),
+    rc = lib.diso_b200_mc_backward(ctypes.c_void_p(256), ctypes.c_void_p(256), 0, 4, 4, 4, 0.0, ctypes.c_void_p(256), None,
                                    ctypes.c_void_p(256), 1, None, ctypes.c_void_p(256), None, None)
     assert rc == -1  # deform without adj_deform

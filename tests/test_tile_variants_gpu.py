@@ -2,7 +2,8 @@
 of 64 consecutive chunks and "listed" tiles over the ordered active-chunk list (sparse surfaces).
 The host picks one from the counts; both must produce identical bits.  Called through the C ABI:
 counts_host == NULL forces the dense flavour, the counts read back after phase 1 select the listed
-one whenever fewer than 75 % of the chunks are active."""
+one whenever fewer than 75 % of the chunks are active.  The same switch selects the backward's sparse path
+(zero fill + list of touched blocks + persistent grid) against its dense one-CTA-per-block launch."""
 import ctypes
 
 import numpy as np
@@ -42,6 +43,7 @@ def test_dense_and_listed_tiles_agree(alg, dtype):
     _lib.check(L.diso_b200_state_layout(alg_id, n, n, n, lay))
     nch = lay[5]
     assert 0 < counts[_lib.CNT_EDGE_CHUNKS] * 4 < nch * 3 and 0 < counts[_lib.CNT_CELL_CHUNKS] * 4 < nch * 3, "input must select the listed flavour"
+    assert counts[_lib.CNT_EDGE_CHUNKS] * 8 < nch, "input must select the sparse (zero fill + touched-block list) backward"
     nv, nf = counts[_lib.CNT_VERTS], counts[_lib.CNT_FACES]
     k = 3 if alg == "mc" else 4
     ne = nv if alg == "mc" else nf
@@ -56,7 +58,7 @@ def test_dense_and_listed_tiles_agree(alg, dtype):
         common = (sdf.data_ptr(), deform.data_ptr(), dt, n, n, n, 0.0, state.data_ptr())
         if alg == "mc":
             _lib.check(L.diso_b200_mc_emit(*common, ch, 1, None, verts.data_ptr(), faces.data_ptr(), st))
-            _lib.check(L.diso_b200_mc_backward(*common, w.data_ptr(), 1, None, adj_s.data_ptr(), adj_d.data_ptr(), st))
+            _lib.check(L.diso_b200_mc_backward(*common, ch, w.data_ptr(), 1, None, adj_s.data_ptr(), adj_d.data_ptr(), st))
         else:
             scratch = torch.empty((ne, 3), dtype=dtype, device=DEV)
             _lib.check(L.diso_b200_dmc_emit(*common, ch, 1, None, scratch.data_ptr(), verts.data_ptr(), faces.data_ptr(), st))
