@@ -67,7 +67,7 @@ __device__ __forceinline__ TilePos make_tile_pos(const Geo &g, int k)
 
 // Phase A for edge lists: thread t owns byte (t & 3) of the three crossing masks of tile entry t >> 2
 // and walks its set bits serially (a few per thread), so list building costs ~15 warp instructions
-// per chunk instead of the ~55 of a lane-per-point formulation (ncu, profiles/r1_final_summary.md).
+// per chunk instead of the ~55 of a lane-per-point formulation (ncu, profiles/r1_v4_summary.md vs r1_final_summary.md).
 // Fills s_list[rank - tile_base], s_pos / s_k (when given); returns the number of edges of the tile
 // (uniform).  Must be called by all CT_THREADS threads; the caller synchronises afterwards.
 // SIGN: bit 13 of each descriptor tells whether the edge's start point is inside (value >= iso), i.e.
