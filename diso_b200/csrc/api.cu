@@ -495,12 +495,24 @@ int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X
                                      static_cast<double *>(adj_sdf), static_cast<double *>(adj_deform), st);
 }
 
+// scratch layout: [0,256) u64 total (number of config-1 quads), u32 ticket at byte 8 ; QuadTileDesc[tiles] ;
+// tile offsets (u32 each) ; flags (1 byte per quad); every part 256-byte aligned
+struct QuadScratch { size_t off_desc, off_tile, off_flags, total; };
+static QuadScratch quad_scratch_layout(int64_t n_quads)
+{
+    const size_t tiles = (size_t)((n_quads + QS_TILE - 1) / QS_TILE);
+    QuadScratch q;
+    q.off_desc = 256;
+    q.off_tile = q.off_desc + align_up(tiles * sizeof(QuadTileDesc) + 16, 256);
+    q.off_flags = q.off_tile + align_up(tiles * 4 + 4, 256);
+    q.total = q.off_flags + align_up((size_t)n_quads + 1, 256);
+    return q;
+}
+
 size_t diso_b200_quad_split_scratch_bytes(int64_t n_quads)
 {
     if (n_quads < 0) return 0;
-    const size_t tiles = (size_t)((n_quads + QS_TILE - 1) / QS_TILE);
-    // [0,256): u64 total ; tile offsets (u32 each, 256-byte aligned) ; flags (1 byte per quad)
-    return 256 + align_up(tiles * 4 + 4, 256) + align_up((size_t)n_quads + 1, 256);
+    return quad_scratch_layout(n_quads).total;
 }
 
 int diso_b200_quad_split(const void *verts, int dtype, const int64_t *quads, int64_t n_quads, void *scratch,
@@ -513,15 +525,18 @@ int diso_b200_quad_split(const void *verts, int dtype, const int64_t *quads, int
     if (!verts || !quads || !scratch || !faces) return fail(DISO_E_INVALID, "null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int tiles = cdiv(n_quads, QS_TILE);
+    const QuadScratch L = quad_scratch_layout(n_quads);
     char *b = static_cast<char *>(scratch);
     unsigned long long *total = reinterpret_cast<unsigned long long *>(b);
-    unsigned *tile_cnt = reinterpret_cast<unsigned *>(b + 256);
-    unsigned char *flags = reinterpret_cast<unsigned char *>(b + 256 + align_up((size_t)tiles * 4 + 4, 256));
+    unsigned *ticket = reinterpret_cast<unsigned *>(b + 8);
+    QuadTileDesc *desc = reinterpret_cast<QuadTileDesc *>(b + L.off_desc);
+    unsigned *tile_off = reinterpret_cast<unsigned *>(b + L.off_tile);
+    unsigned char *flags = reinterpret_cast<unsigned char *>(b + L.off_flags);
     const long long *qd = reinterpret_cast<const long long *>(quads);
-    if (dtype == DISO_F32) LAUNCH("quad_diag", st, quad_diag_kernel<float><<<tiles, QS_TILE, 0, st>>>(static_cast<const float *>(verts), qd, n_quads, flags, tile_cnt));
-    else LAUNCH("quad_diag", st, quad_diag_kernel<double><<<tiles, QS_TILE, 0, st>>>(static_cast<const double *>(verts), qd, n_quads, flags, tile_cnt));
-    LAUNCH("quad_tile_scan", st, tile_scan_kernel<<<1, 1024, 0, st>>>(tile_cnt, tiles, total));
-    LAUNCH("quad_emit", st, quad_emit_kernel<<<tiles, QS_TILE, 0, st>>>(qd, n_quads, flags, tile_cnt, total, reinterpret_cast<long long *>(faces)));
+    CU_TRY(cudaMemsetAsync(b, 0, L.off_tile, st));   // total, ticket, tile descriptors
+    if (dtype == DISO_F32) LAUNCH("quad_diag", st, quad_diag_kernel<float><<<tiles, QS_THREADS, 0, st>>>(static_cast<const float *>(verts), qd, n_quads, flags, tile_off, desc, ticket, total));
+    else LAUNCH("quad_diag", st, quad_diag_kernel<double><<<tiles, QS_THREADS, 0, st>>>(static_cast<const double *>(verts), qd, n_quads, flags, tile_off, desc, ticket, total));
+    LAUNCH("quad_emit", st, quad_emit_kernel<<<tiles, QS_THREADS, 0, st>>>(qd, n_quads, flags, tile_off, total, reinterpret_cast<long long *>(faces)));
     return DISO_OK;
 }
 

@@ -75,8 +75,7 @@ __device__ __forceinline__ void mc_backward_block(const T *__restrict__ sdf, con
     if (tid < BC_ROWS) mine_any = (s_off[tid] | s_off[BC_ROWS + tid] | s_off[2 * BC_ROWS + tid]) != 0u;
     if (!__syncthreads_or(mine_any)) {
         // no crossing edge touches this block (the common case on smooth surfaces): zeros, straight from registers
-        if (OUTPUTS_ZEROED) return;
-        for (int r = wid; r < BC_X * BC_Y; r += BC_THREADS / 32) {
+        for (int r = wid; !OUTPUTS_ZEROED && r < BC_X * BC_Y; r += BC_THREADS / 32) {
             const int ox = r / BC_Y, oy = r - ox * BC_Y;
             const int xp = xp0 + ox, yp = yp0 + oy;
             if (xp > g.X || yp > g.Y) continue;

@@ -1,12 +1,11 @@
-// quad_split.cuh -- DMC quad -> triangle split (diso/__init__.py:118-147) as three small kernels.
+// quad_split.cuh -- DMC quad -> triangle split (diso/__init__.py:118-147) as two kernels.
 //
 // The reference does this with ~60 PyTorch ops and dozens of [Q,3] temporaries.  Here:
 //   Q1 quad_diag_kernel : one thread per quad gathers its 4 vertices, evaluates both diagonals
 //                         (max cosine over the 2x3 triangle angles, cos via x / max(|x|, 1e-12)
-//                         like F.normalize) and records flag = (angles1 < angles2) plus a
-//                         per-tile population count;
-//   Q2 tile_scan_kernel : one CTA turns the tile counts into exclusive offsets (+ total n1);
-//   Q3 quad_emit_kernel : one thread per quad writes its two triangles at the position the
+//                         like F.normalize) and records flag = (angles1 < angles2); the per-tile
+//                         counts are scanned in the same pass (decoupled look-back);
+//   Q2 quad_emit_kernel : one thread per quad writes its two triangles at the position the
 //                         reference's boolean-mask + cat produces: config-1 quads first
 //                         ([0,1,3],[1,2,3]), then config-2 quads ([0,1,2],[0,2,3]), each group
 //                         in quad order.
@@ -17,7 +16,9 @@
 
 namespace diso {
 
-constexpr int QS_TILE = 256;
+constexpr int QS_THREADS = 256;
+constexpr int QS_PER = 1;                       // quads per thread
+constexpr int QS_TILE = QS_THREADS * QS_PER;    // quads per tile; quad (i, tid) of tile t is t*QS_TILE + i*QS_THREADS + tid
 
 __device__ __forceinline__ float sqrt_rn(float x) { return __fsqrt_rn(x); }
 __device__ __forceinline__ double sqrt_rn(double x) { return __dsqrt_rn(x); }
@@ -40,99 +41,168 @@ template <typename T> __device__ __forceinline__ T dot3(const Vec3<T> &a, const 
     s = s + a.z * b.z;
     return s;
 }
-template <typename T> __device__ __forceinline__ T tri_max_cos(const Vec3<T> &v0, const Vec3<T> &v1, const Vec3<T> &v2)
+template <typename T> __device__ __forceinline__ T max3(T a, T b, T c)
 {
-    const T c1 = dot3(unit(v1, v0), unit(v2, v0));
-    const T c2 = dot3(unit(v2, v1), unit(v0, v1));
-    const T c3 = dot3(unit(v0, v2), unit(v1, v2));
-    T m = c1 > c2 ? c1 : c2;
-    return m > c3 ? m : c3;
+    const T m = a > b ? a : b;   // the reference's max over the three angles, same select order
+    return m > c ? m : c;
 }
 
+// One descriptor per tile for the decoupled look-back over the per-tile counts of config-1 quads
+// (same protocol as classify_scan: ticketed tile order, acquire / release flags).
+struct __align__(16) QuadTileDesc {
+    unsigned flag;   // 0 = empty, 1 = aggregate available, 2 = inclusive prefix available
+    unsigned agg;
+    unsigned long long incl;
+};
+
+// Q1: diagonal choice + exclusive prefix of the config-1 counts in one pass.
+//
+// The reference evaluates 4 triangles x 3 angles, each from two freshly normalised edge vectors
+// (24 normalisations: 24 square roots, 72 divisions per quad).  Only six distinct directions exist -- the
+// four sides S0 = 0->1, S1 = 1->2, S2 = 2->3, S3 = 3->0 and the diagonals D0 = 0->2, D1 = 1->3 -- and
+// IEEE arithmetic is sign-symmetric (fl(b-a) = -fl(a-b), x/n and the products of the dot negate exactly),
+// so every cosine of the reference is +-dot(.,.) of two of those six unit vectors, bit for bit:
+//   tri(0,1,3): -S0.S3, -D1.S0, -S3.D1      tri(1,2,3):  S1.D1, -S2.S1,  D1.S2
+//   tri(0,1,2):  S0.D0, -S1.S0,  D0.S1      tri(0,2,3): -D0.S3, -S2.D0, -S3.S2
+// The kernel is bound by the latency of its two dependent loads (quad ids -> vertex gathers; ncu: 40 % issue
+// activity, nothing else above 35 %), so resident warps are what counts: 8 CTAs/SM (32 registers, a few spilled
+// bytes) 2.15 ms at 512^3 vs 2.44 ms at the compiler's 40 registers; several quads per thread cost registers
+// and were slower (2.75 / 3.15 ms for 2 / 4).
 template <typename T>
-__global__ void __launch_bounds__(QS_TILE) quad_diag_kernel(const T *__restrict__ verts, const long long *__restrict__ quads,
-                                                          long long nq, unsigned char *__restrict__ flags,
-                                                          unsigned *__restrict__ tile_cnt)
+__global__ void __launch_bounds__(QS_THREADS, sizeof(T) == 4 ? 8 : 3) quad_diag_kernel(const T *__restrict__ verts, const long long *__restrict__ quads,
+                                                             long long nq, unsigned char *__restrict__ flags,
+                                                             unsigned *__restrict__ tile_off, QuadTileDesc *__restrict__ desc,
+                                                             unsigned *__restrict__ ticket, unsigned long long *__restrict__ total)
 {
-    const long long q = (long long)blockIdx.x * QS_TILE + threadIdx.x;
-    bool f = false;
-    if (q < nq) {
-        const longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(quads + 4 * q));
-        const longlong2 b = __ldg(reinterpret_cast<const longlong2 *>(quads + 4 * q) + 1);
-        Vec3<T> v[4];
-        const long long id[4] = {a.x, a.y, b.x, b.y};
+    __shared__ unsigned s_tile;
+    __shared__ unsigned s_cnt;
+    if (threadIdx.x == 0) { s_tile = atomicAdd(ticket, 1u); s_cnt = 0u; }
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const long long q0 = (long long)tile * QS_TILE + threadIdx.x;
+    // all index loads first, then all vertex gathers: QS_PER independent dependent-load chains per thread
+    // (with one quad per thread the kernel was bound by the latency of that chain: ncu showed 40 % issue
+    // activity and nothing else above 35 %)
+    longlong2 qa[QS_PER], qb[QS_PER];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const T *p = verts + id[i] * 3;
-            v[i] = Vec3<T>{__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+    for (int i = 0; i < QS_PER; ++i) {
+        const long long q = q0 + (long long)i * QS_THREADS;
+        qa[i] = qb[i] = make_longlong2(0, 0);
+        if (q < nq) {
+            qa[i] = __ldg(reinterpret_cast<const longlong2 *>(quads + 4 * q));
+            qb[i] = __ldg(reinterpret_cast<const longlong2 *>(quads + 4 * q) + 1);
         }
-        const T t13a = tri_max_cos(v[0], v[1], v[3]), t13b = tri_max_cos(v[1], v[2], v[3]);
-        const T t02a = tri_max_cos(v[0], v[1], v[2]), t02b = tri_max_cos(v[0], v[2], v[3]);
+    }
+    Vec3<T> v[QS_PER][4];
+#pragma unroll
+    for (int i = 0; i < QS_PER; ++i) {
+        const long long id[4] = {qa[i].x, qa[i].y, qb[i].x, qb[i].y};   // (out-of-range quads read vertex 0)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const T *p = verts + id[c] * 3;
+            v[i][c] = Vec3<T>{__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+        }
+    }
+    unsigned mine = 0;
+#pragma unroll
+    for (int i = 0; i < QS_PER; ++i) {
+        const long long q = q0 + (long long)i * QS_THREADS;
+        const Vec3<T> S0 = unit(v[i][1], v[i][0]), S1 = unit(v[i][2], v[i][1]), S2 = unit(v[i][3], v[i][2]), S3 = unit(v[i][0], v[i][3]);
+        const Vec3<T> D0 = unit(v[i][2], v[i][0]), D1 = unit(v[i][3], v[i][1]);
+        const T t13a = max3(-dot3(S0, S3), -dot3(D1, S0), -dot3(S3, D1));
+        const T t13b = max3(dot3(S1, D1), -dot3(S2, S1), dot3(D1, S2));
+        const T t02a = max3(dot3(S0, D0), -dot3(S1, S0), dot3(D0, S1));
+        const T t02b = max3(-dot3(D0, S3), -dot3(S2, D0), -dot3(S3, S2));
         const T a1 = t13a > t13b ? t13a : t13b;
         const T a2 = t02a > t02b ? t02a : t02b;
-        f = a1 < a2;
-        flags[q] = f ? 1 : 0;
+        const bool f = q < nq && a1 < a2;
+        if (q < nq) flags[q] = f ? 1 : 0;
+        mine += f ? 1u : 0u;
     }
-    const int c = __syncthreads_count(f);
-    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = (unsigned)c;
-}
-
-// exclusive scan of n u32 values in place by ONE CTA; total -> *total_out (u64)
-__global__ void __launch_bounds__(1024) tile_scan_kernel(unsigned *__restrict__ v, int n, unsigned long long *__restrict__ total_out)
-{
-    __shared__ unsigned long long s_part[1024];
-    const int tid = threadIdx.x;
-    const int per = (n + 1023) / 1024;
-    const int lo = min(n, tid * per), hi = min(n, lo + per);
-    unsigned long long s = 0;
-    for (int i = lo; i < hi; ++i) s += v[i];
-    s_part[tid] = s;
+    mine = __reduce_add_sync(FULL, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_cnt, mine);
     __syncthreads();
-    // Hillis-Steele inclusive scan over the 1024 partials
-    for (int d = 1; d < 1024; d <<= 1) {
-        unsigned long long t = tid >= d ? s_part[tid - d] : 0ull;
-        __syncthreads();
-        s_part[tid] += t;
-        __syncthreads();
+    const unsigned cnt = s_cnt;
+    // ---- decoupled look-back over the tile counts (warp 0) ------------------------------------
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            if (lane == 0) { st_relaxed_u64(&desc[0].incl, cnt); st_release_u32(&desc[0].flag, 2u); }
+        } else {
+            if (lane == 0) { desc[tile].agg = cnt; st_release_u32(&desc[tile].flag, 1u); }
+            int base = (int)tile - 1;
+            while (true) {
+                const int t = base - lane;
+                unsigned fl = 2u;
+                unsigned long long x = 0;
+                if (t >= 0) {
+                    do { fl = ld_acquire_u32(&desc[t].flag); } while (fl == 0u);
+                    x = fl == 2u ? ld_relaxed_u64(&desc[t].incl) : (unsigned long long)*reinterpret_cast<volatile unsigned *>(&desc[t].agg);
+                }
+                const unsigned m = __ballot_sync(FULL, fl == 2u);
+                const int stop = m ? (__ffs(m) - 1) : 32;   // nearest predecessor with an inclusive prefix
+                if (lane > stop) x = 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(FULL, x, d);
+                excl += x;
+                if (m) break;
+                base -= 32;
+            }
+            if (lane == 0) { st_relaxed_u64(&desc[tile].incl, excl + cnt); st_release_u32(&desc[tile].flag, 2u); }
+        }
+        if (lane == 0) {
+            tile_off[tile] = (unsigned)excl;   // < 2^32: callers cap n_quads
+            if ((long long)(tile + 1) * QS_TILE >= nq) *total = excl + cnt;   // last tile: number of config-1 quads
+        }
     }
-    unsigned long long run = s_part[tid] - s;
-    for (int i = lo; i < hi; ++i) {
-        const unsigned c = v[i];
-        v[i] = (unsigned)run;  // < 2^32: callers cap n_quads
-        run += c;
-    }
-    if (tid == 1023) *total_out = s_part[1023];
 }
 
-__global__ void __launch_bounds__(QS_TILE) quad_emit_kernel(const long long *__restrict__ quads, long long nq,
-                                                          const unsigned char *__restrict__ flags,
-                                                          const unsigned *__restrict__ tile_off,
-                                                          const unsigned long long *__restrict__ total,
-                                                          long long *__restrict__ faces)
+__global__ void __launch_bounds__(QS_THREADS) quad_emit_kernel(const long long *__restrict__ quads, long long nq,
+                                                             const unsigned char *__restrict__ flags,
+                                                             const unsigned *__restrict__ tile_off,
+                                                             const unsigned long long *__restrict__ total,
+                                                             long long *__restrict__ faces)
 {
-    __shared__ unsigned s_w[QS_TILE / 32];
+    __shared__ unsigned s_w[QS_PER][QS_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long q = (long long)blockIdx.x * QS_TILE + tid;
-    const bool f = q < nq && flags[q];
-    const unsigned bal = __ballot_sync(FULL, f);
-    if (lane == 0) s_w[wid] = __popc(bal);
+    const long long q0 = (long long)blockIdx.x * QS_TILE + tid;
+    bool f[QS_PER];
+    unsigned bal[QS_PER];
+#pragma unroll
+    for (int i = 0; i < QS_PER; ++i) {
+        const long long q = q0 + (long long)i * QS_THREADS;
+        f[i] = q < nq && flags[q];
+        bal[i] = __ballot_sync(FULL, f[i]);
+        if (lane == 0) s_w[i][wid] = __popc(bal[i]);
+    }
     __syncthreads();
-    unsigned before = tile_off[blockIdx.x] + __popc(bal & lanemask_lt(lane));
-    for (int i = 0; i < wid; ++i) before += s_w[i];
-    if (q >= nq) return;
     const long long n1 = (long long)*total;
-    const longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(quads + 4 * q));
-    const longlong2 b = __ldg(reinterpret_cast<const longlong2 *>(quads + 4 * q) + 1);
-    const long long pos = f ? (long long)before : n1 + (q - (long long)before);
-    longlong2 *dst = reinterpret_cast<longlong2 *>(faces + pos * 6);
-    if (f) {  // [0,1,3] [1,2,3]
-        __stcs(dst, make_longlong2(a.x, a.y));
-        __stcs(dst + 1, make_longlong2(b.y, a.y));
-        __stcs(dst + 2, make_longlong2(b.x, b.y));
-    } else {  // [0,1,2] [0,2,3]
-        __stcs(dst, make_longlong2(a.x, a.y));
-        __stcs(dst + 1, make_longlong2(b.x, a.x));
-        __stcs(dst + 2, make_longlong2(b.x, b.y));
+    unsigned run = tile_off[blockIdx.x];   // config-1 quads before this tile; quads are ranked in (i, tid) order == quad order
+#pragma unroll
+    for (int i = 0; i < QS_PER; ++i) {
+        unsigned before = run + __popc(bal[i] & lanemask_lt(lane));
+#pragma unroll
+        for (int w = 0; w < QS_THREADS / 32; ++w) {
+            const unsigned c = s_w[i][w];
+            if (w < wid) before += c;
+            run += c;
+        }
+        const long long q = q0 + (long long)i * QS_THREADS;
+        if (q >= nq) continue;
+        const longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(quads + 4 * q));
+        const longlong2 b = __ldg(reinterpret_cast<const longlong2 *>(quads + 4 * q) + 1);
+        const long long pos = f[i] ? (long long)before : n1 + (q - (long long)before);
+        longlong2 *dst = reinterpret_cast<longlong2 *>(faces + pos * 6);
+        if (f[i]) {  // [0,1,3] [1,2,3]
+            __stcs(dst, make_longlong2(a.x, a.y));
+            __stcs(dst + 1, make_longlong2(b.y, a.y));
+            __stcs(dst + 2, make_longlong2(b.x, b.y));
+        } else {  // [0,1,2] [0,2,3]
+            __stcs(dst, make_longlong2(a.x, a.y));
+            __stcs(dst + 1, make_longlong2(b.x, a.x));
+            __stcs(dst + 2, make_longlong2(b.x, b.y));
+        }
     }
 }
 

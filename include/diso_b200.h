@@ -135,7 +135,7 @@ int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X
                            const void *adj_verts, int normalize, const diso_b200_frame *frame,
                            int grad_mode, void *scratch, void *adj_sdf, void *adj_deform, void *stream);
 
-/* Quad -> triangle split of diso/__init__.py:118-147 as three small kernels (no PyTorch
+/* Quad -> triangle split of diso/__init__.py:118-147 as two kernels (no PyTorch
  * temporaries).  verts [n_verts,3] dtype (API frame), quads [n_quads,4] int64, faces
  * [2*n_quads,3] int64.  scratch: caller-owned, diso_b200_quad_split_scratch_bytes(n_quads).
  * Output order == the reference's mask + cat: all quads whose first diagonal wins
