@@ -317,7 +317,8 @@ int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, co
     static const int force = env_int("DISO_BWD_SPARSE", -1);   // experiment knob: 0 / 1 force the path
     bool sparse = counts_host && counts_host[DISO_CNT_EDGE_CHUNKS] * 8 < (long long)g.NCH;
     if (force >= 0) sparse = force != 0;
-    // block shape from a sweep on B200 (512^3 rand-flexi): 4x8 1.72 ms, 3x8 / 4x6 1.69, 8x4 1.76, 6x8 1.82, 4x4 1.92
+    // block shape (common.cuh: BWD_BX x BWD_BY) from sweeps on B200 (512^3 rand-flexi): 4x6 1.70 ms, 3x8 1.71, 4x7 / 4x8 1.73,
+    // 8x4 1.76, 6x8 1.82, 2x8 1.90, 4x4 1.92
     if (deform) return launch_bwd_compact<T, true, BWD_BX, BWD_BY>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, adj_verts, adj_sdf, adj_deform, p.bwd, sparse, st);
     return launch_bwd_compact<T, false, BWD_BX, BWD_BY>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, adj_verts, adj_sdf, adj_deform, p.bwd, sparse, st);
 }

@@ -66,7 +66,11 @@ struct __align__(64) TileDesc {
 };
 
 constexpr int SCAN_TILE = 256;  // chunks per scan tile == threads per classify CTA
-constexpr int BWD_BX = 4, BWD_BY = 8;  // rows per backward block (x, y); one 32-point chunk in z
+#ifndef DISO_BWD_BX
+#define DISO_BWD_BX 4
+#define DISO_BWD_BY 6
+#endif
+constexpr int BWD_BX = DISO_BWD_BX, BWD_BY = DISO_BWD_BY;  // rows per backward block (x, y); one 32-point chunk in z
 
 // Byte offsets of the arrays inside the caller-owned state buffer.
 struct StateLayout {
