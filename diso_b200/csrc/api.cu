@@ -278,8 +278,8 @@ int launch_bwd_compact(const T *sdf, const T *deform, const Geo &g, T isoT, T pa
     const long long nblk = (long long)ntx * nty * g.NC;
     // L1 capacity matters more than occupancy here (the gathers of sdf / deform / adjoints hit L1 ~63 %): with the
     // driver's default carve-out (8 CTAs/SM, ~28 KB L1) the fp32 kernel takes 2.48 ms at 512^3, with 132 KB of
-    // shared memory (5 CTAs, ~124 KB L1) 1.72 ms; fp64: 3.18 ms at 72 % vs 4.59 ms at 100 % (sweeps in DESIGN.md)
-    const int carve = sizeof(T) == 4 ? 58 : 72;
+    // shared memory (~124 KB L1) 1.70 ms; fp64: 2.91 ms at 58-65 % vs 4.53 ms at 86 % (sweeps in DESIGN.md)
+    const int carve = 58;
     if (sparse) {
         // zero fill + list of the touched blocks + persistent grid over that list (mc_backward_compact.cuh)
         auto kern = mc_backward_queue_kernel<T, HAS_DEF, BX, BY>;
