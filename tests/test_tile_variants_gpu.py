@@ -69,3 +69,32 @@ def test_dense_and_listed_tiles_agree(alg, dtype):
     for a, b, what in zip(res[0], res[1], ("verts", "faces", "adj_sdf", "adj_deform")):
         assert not np.isnan(a.astype(np.float64)).any() and (a != -1).any(), what + ": not fully written"
         assert np.array_equal(a, b), what + ": listed and dense tile flavours differ"
+
+
+def test_sparse_and_dense_backward_agree_at_scale():
+    """Sphere 448^3 (a smooth surface: ~10 % of the chunks own a crossing edge): the zero-fill + touched-block
+    path and the one-CTA-per-block path must write identical gradients, zeros included."""
+    import diso_b200
+    from diso_b200 import _lib, synthetic as syn
+    L = _lib.load()
+    n = 448
+    sdf = syn.sphere_sdf(n).to(DEV)
+    deform = syn.random_deform(n, 3).to(DEV)
+    state, counts = diso_b200._count(_lib.ALG_MC, sdf, 0.0)
+    lay = (ctypes.c_int64 * 8)()
+    _lib.check(L.diso_b200_state_layout(_lib.ALG_MC, n, n, n, lay))
+    assert counts[_lib.CNT_EDGE_CHUNKS] * 8 < lay[5]
+    nv = counts[_lib.CNT_VERTS]
+    w = torch.cos(torch.arange(nv * 3, dtype=torch.float64, device=DEV).reshape(nv, 3) * 0.618).float()
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for ch in (ctypes.cast(_lib.counts_array(counts), ctypes.c_void_p), None):
+        adj_s = torch.full_like(sdf, float("nan"))
+        adj_d = torch.full_like(deform, float("nan"))
+        _lib.check(L.diso_b200_mc_backward(sdf.data_ptr(), deform.data_ptr(), _lib.F32, n, n, n, 0.0, state.data_ptr(), ch,
+                                           w.data_ptr(), 1, None, adj_s.data_ptr(), adj_d.data_ptr(), st))
+        torch.cuda.synchronize()
+        outs.append((adj_s, adj_d))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert bool(torch.isfinite(outs[0][1]).all()) and float(outs[0][1].abs().sum()) > 0
+    assert int((outs[0][0] != 0).sum()) < sdf.numel() // 10   # mostly zeros, all written
