@@ -461,6 +461,14 @@ __global__ void __launch_bounds__(SCAN_TILE, 8)   // 32 registers: 8 CTAs/SM hid
             for (int q = 0; q < 4; ++q) s_excl[q] = e[q];
             if (s_used_tot) atomicAdd((unsigned long long *)&counts[DISO_CNT_USED], (unsigned long long)s_used_tot);
         }
+    } else if (s_any_cells) {
+        // Meanwhile warps 1..7 flush the staged per-cell words (they do not depend on the prefix): 16 words (32 cells)
+        // per chunk, coalesced.  A scan tile without used cells is skipped (its words are never read), so sparse
+        // surfaces write almost nothing.  (Before, all eight warps waited at the barrier below for warp 0's look-back:
+        // ncu showed 19 % of the issue slots stalled on it.)
+        unsigned *cout = reinterpret_cast<unsigned *>(C) + (size_t)tile * SCAN_TILE * 16;
+        const int rows = min(SCAN_TILE, g.NCH - tile * SCAN_TILE);
+        for (int i = tid - 32; i < rows * 16; i += SCAN_TILE - 32) cout[i] = s_cw[(i >> 4) * CW_STRIDE + (i & 15)];
     }
     __syncthreads();
     const unsigned long long base_a = s_excl[0] + (excl_local & 0xffffull);
@@ -468,13 +476,6 @@ __global__ void __launch_bounds__(SCAN_TILE, 8)   // 32 registers: 8 CTAs/SM hid
     const unsigned long long base_c = s_excl[2] + ((excl_local >> 32) & 0xffffull);
     const unsigned long long base_d = s_excl[3] + (excl_local >> 48);
 
-    // flush the staged per-cell words: 16 words (32 cells) per chunk, coalesced; a scan tile without
-    // used cells is skipped (its words are never read), so sparse surfaces write almost nothing
-    if (s_any_cells) {
-        unsigned *cout = reinterpret_cast<unsigned *>(C) + (size_t)tile * SCAN_TILE * 16;
-        const int rows = min(SCAN_TILE, g.NCH - tile * SCAN_TILE);
-        for (int i = tid; i < rows * 16; i += SCAN_TILE) cout[i] = s_cw[(i >> 4) * CW_STRIDE + (i & 15)];
-    }
     // ordered active-chunk lists (ascending chunk id): what the emit kernels iterate over
     if (k < g.NCH) {
         if (na) active[base_c] = (unsigned)k;
