@@ -23,23 +23,23 @@ constexpr int QS_TILE = QS_THREADS * QS_PER;    // quads per tile; quad (i, tid)
 __device__ __forceinline__ float sqrt_rn(float x) { return __fsqrt_rn(x); }
 __device__ __forceinline__ double sqrt_rn(double x) { return __dsqrt_rn(x); }
 
+// Summation order of torch's CUDA reductions over a row of 3 (measured on B200 with tools/probe_torch_reduce.py,
+// torch 2.11: the reduce kernel gives the row to two threads -- elements {0, 2} and {1} -- and combines them with
+// one shuffle): vector_norm = sqrt((x^2 + z^2) + y^2) and sum = (p0 + p2) + p1, every square / product rounded on its
+// own (no FMA).  Reproducing that order makes every cosine of the reference bit-identical, so the diagonal choice
+// agrees on ALL quads, ties included (35 494 of 72.5 M quads flipped at 512^3 with the x,y,z FMA chain used before).
 template <typename T> __device__ __forceinline__ Vec3<T> unit(const Vec3<T> &a, const Vec3<T> &b)
 {
-    // F.normalize(a - b): v / max(||v||_2, 1e-12)
+    // F.normalize(a - b): v / max(||v||_2, 1e-12)   (diso/__init__.py:126-128)
     Vec3<T> v{a.x - b.x, a.y - b.y, a.z - b.z};
-    T n2 = v.x * v.x;
-    n2 = fma_rn(v.y, v.y, n2);
-    n2 = fma_rn(v.z, v.z, n2);
+    const T n2 = (v.x * v.x + v.z * v.z) + v.y * v.y;
     T n = sqrt_rn(n2);
     n = n > T(1e-12) ? n : T(1e-12);
     return Vec3<T>{v.x / n, v.y / n, v.z / n};
 }
 template <typename T> __device__ __forceinline__ T dot3(const Vec3<T> &a, const Vec3<T> &b)
 {
-    T s = a.x * b.x;
-    s = s + a.y * b.y;
-    s = s + a.z * b.z;
-    return s;
+    return (a.x * b.x + a.z * b.z) + a.y * b.y;
 }
 template <typename T> __device__ __forceinline__ T max3(T a, T b, T c)
 {

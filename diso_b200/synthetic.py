@@ -1,7 +1,7 @@
 """Seeded synthetic SDF inputs (BASELINE.md section 2 / SURVEY.md section 8d).
 
 Everything is generated on the CPU with an explicit ``torch.Generator`` so that every
-implementation (reference CUDA build, CPU oracle, this library) and every GPU sees identical
+implementation (reference CUDA build, CPU restatement, this library) and every GPU sees identical
 bits; callers move the tensors to the device.
 """
 import torch

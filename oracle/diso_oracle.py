@@ -178,15 +178,21 @@ def split_quads(verts, quads):
     dt = verts.dtype
     quads = quads.astype(np.int64)
 
+    def sum3(p):
+        # torch's CUDA reduction over a row of 3 adds (p0 + p2) + p1, each product rounded on its own
+        # (measured on B200, tools/probe_torch_reduce.py); with this order the diagonal choice of the
+        # reference is reproduced on every quad, ties included
+        return ((p[..., 0] + p[..., 2]).astype(dt) + p[..., 1]).astype(dt)
+
     def nrm(x):
-        n = np.sqrt((x * x).sum(-1, dtype=dt)).astype(dt)
-        return x / np.maximum(n, dt.type(1e-12))[..., None]
+        n = np.sqrt(sum3((x * x).astype(dt))).astype(dt)
+        return (x / np.maximum(n, dt.type(1e-12))[..., None]).astype(dt)
 
     def tri_max_cos(idx):
         v0, v1, v2 = (verts[quads[:, j]] for j in idx)
-        c1 = (nrm(v1 - v0) * nrm(v2 - v0)).sum(-1, dtype=dt)
-        c2 = (nrm(v2 - v1) * nrm(v0 - v1)).sum(-1, dtype=dt)
-        c3 = (nrm(v0 - v2) * nrm(v1 - v2)).sum(-1, dtype=dt)
+        c1 = sum3((nrm(v1 - v0) * nrm(v2 - v0)).astype(dt))
+        c2 = sum3((nrm(v2 - v1) * nrm(v0 - v1)).astype(dt))
+        c3 = sum3((nrm(v0 - v2) * nrm(v1 - v2)).astype(dt))
         return np.maximum(np.maximum(c1, c2), c3)
 
     a1 = np.maximum(tri_max_cos([0, 1, 3]), tri_max_cos([1, 2, 3]))
