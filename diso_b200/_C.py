@@ -81,12 +81,12 @@ class _Base:
             if self._alg == _lib.ALG_MC:
                 _lib.check(L.diso_b200_mc_backward(grid.data_ptr(), p(deform), dt, X, Y, Z, float(iso), state.data_ptr(),
                                                    ctypes.cast(counts_c, ctypes.c_void_p),
-                                                   adj_verts.data_ptr(), 0, None, g_grid.data_ptr(), p(g_def), st))
+                                                   adj_verts.data_ptr(), 0, None, None, 0, g_grid.data_ptr(), p(g_def), st))
             else:
                 scratch = torch.empty((max(nf, 1), 3), dtype=self._dtype, device=grid.device)
                 _lib.check(L.diso_b200_dmc_backward(grid.data_ptr(), p(deform), dt, X, Y, Z, float(iso), state.data_ptr(),
                                                     ctypes.cast(counts_c, ctypes.c_void_p),
-                                                    adj_verts.data_ptr(), 0, None, _lib.GRAD_REFERENCE, scratch.data_ptr(),
+                                                    adj_verts.data_ptr(), 0, None, _lib.GRAD_REFERENCE, None, 0, scratch.data_ptr(),
                                                     g_grid.data_ptr(), p(g_def), st))
             adj_grid.add_(g_grid)          # the reference accumulates into the caller's buffers (atomicAdd)
             if adj_deform is not None:

@@ -30,6 +30,11 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _blocks32(n):
+    """Per-edge side arrays (saved edge records, DMC edge adjoints) are stored in groups of 32 edges."""
+    return max((n + 31) // 32, 1)
+
+
 def _check_inputs(grid, deform, dtype):
     # mirrors the checks of the reference glue (src/pybind.cpp:5-11,57-60): CUDA tensors of the
     # extractor's dtype.  Contiguity is not required of the caller (the reference's F.pad makes a
@@ -49,6 +54,19 @@ def _check_inputs(grid, deform, dtype):
             raise DisoB200Error("deform must have shape [X,Y,Z,3], got %s" % (tuple(deform.shape),))
 
 
+_pinned = {}   # thread id -> pinned int64[COUNT_SLOTS] receiving the count block (one small D2H per forward)
+
+
+def _pinned_counts():
+    import threading
+    key = threading.get_ident()
+    buf = _pinned.get(key)
+    if buf is None:
+        t = torch.empty(_lib.COUNT_SLOTS, dtype=torch.int64).pin_memory()
+        buf = _pinned[key] = (t, (ctypes.c_int64 * _lib.COUNT_SLOTS).from_address(t.data_ptr()))
+    return buf
+
+
 def _count(alg, grid, isovalue):
     """Phase 1 + the forward's single host sync.  Returns (state tensor, counts list)."""
     L = _lib.load()
@@ -57,10 +75,12 @@ def _count(alg, grid, isovalue):
     if nbytes == 0:
         _lib.check(-1 if not L.diso_b200_last_error() else -4)
     state = torch.empty(nbytes, dtype=torch.uint8, device=grid.device)
+    st = _stream()
     _lib.check(L.diso_b200_count(alg, grid.data_ptr(), _DTYPES[grid.dtype], X, Y, Z, float(isovalue),
-                                 state.data_ptr(), nbytes, _stream()))
-    counts = state[: 8 * _lib.COUNT_SLOTS].view(torch.int64).cpu().tolist()  # the one sync
-    return state, counts
+                                 state.data_ptr(), nbytes, st))
+    pinned, view = _pinned_counts()
+    _lib.check(L.diso_b200_read_counts(state.data_ptr(), pinned.data_ptr(), st))   # the one sync
+    return state, list(view)
 
 
 class _Extract(Function):
@@ -81,16 +101,26 @@ class _Extract(Function):
         ctx.counts = _lib.counts_array(counts)   # host copy of the count block: sizes the emit / backward launches
         verts = torch.empty((n_verts, 3), dtype=grid.dtype, device=grid.device)
         faces = torch.empty((n_faces, k), dtype=torch.int64, device=grid.device)
+        n_edges = n_verts if alg == _lib.ALG_MC else n_faces
+        # saved edge records (include/diso_b200.h: edge_rec): only when a gradient can be asked for later
+        rec = None
+        if ctx.needs_input_grad[0] or (deform is not None and ctx.needs_input_grad[1]):
+            rec = torch.empty((_blocks32(n_edges), 5, 32), dtype=grid.dtype, device=grid.device)
         args = (grid.data_ptr(), _ptr(deform), _DTYPES[grid.dtype], X, Y, Z, float(isovalue), state.data_ptr(),
                 ctypes.cast(ctx.counts, ctypes.c_void_p), int(bool(normalize)), _lib.frame_ptr(ctx.frame))
         if alg == _lib.ALG_MC:
-            _lib.check(L.diso_b200_mc_emit(*args, verts.data_ptr(), faces.data_ptr(), _stream()))
+            _lib.check(L.diso_b200_mc_emit(*args, verts.data_ptr(), faces.data_ptr(), _ptr(rec), max(n_edges, 1), _stream()))
         else:
             scratch = torch.empty((max(n_faces, 1), 3), dtype=grid.dtype, device=grid.device)  # edge crossings
-            _lib.check(L.diso_b200_dmc_emit(*args, scratch.data_ptr(), verts.data_ptr(), faces.data_ptr(), _stream()))
+            _lib.check(L.diso_b200_dmc_emit(*args, scratch.data_ptr(), verts.data_ptr(), faces.data_ptr(), _ptr(rec),
+                                            max(n_edges, 1), _stream()))
         ctx.alg, ctx.isovalue, ctx.normalize, ctx.grad_mode = alg, float(isovalue), bool(normalize), grad_mode
-        ctx.n_edges = n_verts if alg == _lib.ALG_MC else n_faces
-        ctx.save_for_backward(grid, deform, state)
+        ctx.n_edges = n_edges
+        ctx.has_rec = rec is not None
+        if rec is not None:
+            ctx.save_for_backward(grid, deform, state, rec)
+        else:
+            ctx.save_for_backward(grid, deform, state)
         ctx.mark_non_differentiable(faces)
         # do not let autograd allocate + fill a zero "gradient" for the (multi-GB) int64 faces output
         ctx.set_materialize_grads(False)
@@ -98,34 +128,42 @@ class _Extract(Function):
 
     @staticmethod
     def backward(ctx, adj_verts, adj_faces):
-        grid, deform, state = ctx.saved_tensors
+        if ctx.has_rec:
+            grid, deform, state, rec = ctx.saved_tensors
+        else:
+            (grid, deform, state), rec = ctx.saved_tensors, None
         L = _lib.load()
         X, Y, Z = grid.shape
+        need_grid = ctx.needs_input_grad[0]
+        need_deform = deform is not None and ctx.needs_input_grad[1]
+        none7 = (None,) * 7
         if adj_verts is None:  # verts did not take part in the loss: all gradients are zero
-            return (torch.zeros_like(grid), torch.zeros_like(deform) if deform is not None else None,
-                    None, None, None, None, None, None, None)
+            return (torch.zeros_like(grid) if need_grid else None, torch.zeros_like(deform) if need_deform else None) + none7
         # the reference requires a contiguous adj_verts and raises otherwise (pybind.cpp:142);
         # expanded gradients (e.g. from verts.sum() with normalize=False) are made contiguous here.
         adj_verts = adj_verts.contiguous()
-        need_grid, need_deform = ctx.needs_input_grad[0], deform is not None
         with torch.cuda.device(grid.device):
-            adj_grid = torch.empty_like(grid)  # fully written by the kernel, zeros included
-            adj_deform = torch.empty_like(deform) if need_deform else None
+            # fully written by the kernel, zeros included; an input that needs no gradient gets no buffer at all
+            # (the saved-record backward skips that output; without records both are required by the ABI)
+            want_grid = need_grid or rec is None
+            want_deform = need_deform or (rec is None and deform is not None)
+            adj_grid = torch.empty_like(grid) if want_grid else None
+            adj_deform = torch.empty_like(deform) if want_deform else None
             dt = _DTYPES[grid.dtype]
             if ctx.alg == _lib.ALG_MC:
                 _lib.check(L.diso_b200_mc_backward(grid.data_ptr(), _ptr(deform), dt, X, Y, Z, ctx.isovalue,
                                                    state.data_ptr(), ctypes.cast(ctx.counts, ctypes.c_void_p),
                                                    adj_verts.data_ptr(), int(ctx.normalize),
-                                                   _lib.frame_ptr(ctx.frame), adj_grid.data_ptr(), _ptr(adj_deform), _stream()))
+                                                   _lib.frame_ptr(ctx.frame), _ptr(rec), max(ctx.n_edges, 1),
+                                                   _ptr(adj_grid), _ptr(adj_deform), _stream()))
             else:
-                scratch = torch.empty((max(ctx.n_edges, 1), 3), dtype=grid.dtype, device=grid.device)
+                scratch = torch.empty((_blocks32(ctx.n_edges), 3, 32), dtype=grid.dtype, device=grid.device)  # per-edge adjoints
                 _lib.check(L.diso_b200_dmc_backward(grid.data_ptr(), _ptr(deform), dt, X, Y, Z, ctx.isovalue,
                                                     state.data_ptr(), ctypes.cast(ctx.counts, ctypes.c_void_p),
                                                     adj_verts.data_ptr(), int(ctx.normalize), _lib.frame_ptr(ctx.frame),
-                                                    ctx.grad_mode, scratch.data_ptr(), adj_grid.data_ptr(),
-                                                    _ptr(adj_deform), _stream()))
-        del need_grid
-        return adj_grid, adj_deform, None, None, None, None, None, None, None
+                                                    ctx.grad_mode, _ptr(rec), max(ctx.n_edges, 1), scratch.data_ptr(),
+                                                    _ptr(adj_grid), _ptr(adj_deform), _stream()))
+        return (adj_grid if need_grid else None, adj_deform if need_deform else None) + none7
 
 
 def _run(alg, dtype, grad_mode, grid, deform, isovalue, normalize, want_state=False, slab_mode=False):

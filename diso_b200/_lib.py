@@ -40,10 +40,11 @@ SIGNATURES = {
     "diso_b200_state_bytes": (_sz, [_i, _i, _i, _i]),
     "diso_b200_state_layout": (_i, [_i, _i, _i, _i, ctypes.POINTER(ctypes.c_int64)]),
     "diso_b200_count": (_i, [_i, _vp, _i, _i, _i, _i, _d, _vp, _sz, _vp]),
-    "diso_b200_mc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
-    "diso_b200_dmc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
-    "diso_b200_mc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
-    "diso_b200_dmc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "diso_b200_read_counts": (_i, [_vp, _vp, _vp]),
+    "diso_b200_mc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "diso_b200_dmc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "diso_b200_mc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "diso_b200_dmc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _i, _vp, _i, _vp, _i64, _vp, _vp, _vp, _vp]),
     "diso_b200_quad_split_scratch_bytes": (_sz, [_i64]),
     "diso_b200_quad_split": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp]),
     "diso_b200_debug_cell_codes": (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
@@ -72,7 +73,7 @@ def load():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.diso_b200_abi_version() != 2:
+        if L.diso_b200_abi_version() != 3:
             raise DisoB200Error("libdiso_b200.so ABI version mismatch")
         _lib = L
     return _lib

@@ -7,7 +7,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
-#include <set>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -15,6 +15,7 @@
 #include "compact.cuh"
 #include "dmc_compact.cuh"
 #include "mc_backward_compact.cuh"
+#include "mc_backward_v2.cuh"
 #include "quad_split.cuh"
 
 using namespace diso;
@@ -139,17 +140,29 @@ inline int env_int(const char *name, int dflt)
 
 inline void kernel_attrs(const void *fn, const char *env, int carveout_pct, size_t dyn_smem = 0)
 {
+    // (device, kernel) -> largest dynamic shared-memory size opted into so far.  The opt-in is re-applied whenever a
+    // call needs more than any earlier one did (a long-row grid after a short-row one), so the outcome no longer
+    // depends on the call history; the carve-out preference is set on first use only.
     static std::mutex mu;
-    static std::set<std::pair<int, const void *>> done;
+    static std::map<std::pair<int, const void *>, size_t> done;
     int dev = 0;
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lk(mu);
-    if (!done.insert(std::make_pair(dev, fn)).second) return;
+    auto it = done.find(std::make_pair(dev, fn));
+    const bool first = it == done.end();
+    if (!first && dyn_smem <= it->second) return;
     if (dyn_smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
-    const int pct = env_int(env, carveout_pct);
-    if (pct >= 0) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(pct, 100));
+    if (first) {
+        const int pct = env_int(env, carveout_pct);
+        if (pct >= 0) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(pct, 100));
+        done[std::make_pair(dev, fn)] = dyn_smem;
+    } else {
+        it->second = dyn_smem;
+    }
     cudaGetLastError();
 }
+
+constexpr size_t MAX_OPTIN_SMEM = 227 * 1024;   // sm_100: 227 KB per CTA
 
 // ---- tracing: launch counter + optional per-kernel CUDA-event timing (per host thread) --------
 std::atomic<long long> g_launches{0};
@@ -187,25 +200,27 @@ template <typename F> int launch(const char *name, cudaStream_t st, F &&f)
 template <typename T>
 int count_impl(int alg, const T *sdf, const Geo &g, double iso, const StateLayout &L, const StatePtrs &p, cudaStream_t st)
 {
-    // header (counts, ticket, tile descriptors) = 0; sign tail = ones; record tails = 0
+    // header (counts, ticket, tile descriptors) = 0: the one memset of the count phase.  The array tails (sign tail =
+    // ones, record tails = 0) are written by the sign pass (classify.cuh:fill_tails) -- three launches fewer per call.
     CU_TRY(cudaMemsetAsync(p.counts, 0, L.off_sign - L.off_counts, st));
-    CU_TRY(cudaMemsetAsync(p.S + g.NCH, 0xff, (size_t)L.sign_tail * 4, st));
-    CU_TRY(cudaMemsetAsync(p.E + g.NCH, 0, (size_t)L.rec_tail * 16, st));
-    if (alg == DISO_ALG_MC) CU_TRY(cudaMemsetAsync(reinterpret_cast<uint2 *>(p.aux) + g.NCH, 0, 8 * 8, st));
-    else CU_TRY(cudaMemsetAsync(reinterpret_cast<uint4 *>(p.aux) + g.NCH, 0, (size_t)L.rec_tail * 16, st));
+    TailFill tf;
+    tf.s_tail = p.S + g.NCH; tf.n_s = L.sign_tail;
+    tf.e_tail = p.E + g.NCH; tf.n_e = L.rec_tail;
+    if (alg == DISO_ALG_MC) { tf.aux_tail = reinterpret_cast<uint2 *>(p.aux) + g.NCH; tf.n_aux = 8; }
+    else { tf.aux_tail = reinterpret_cast<uint2 *>(reinterpret_cast<uint4 *>(p.aux) + g.NCH); tf.n_aux = 2 * L.rec_tail; }
 
     const T isoT = (T)iso;
     const int warps = 8;
     constexpr int VN = 16 / (int)sizeof(T);   // values per 128-bit load
-    const bool vec = (g.Z % VN == 0) && ((reinterpret_cast<uintptr_t>(sdf) & 15) == 0);
+    const int NA = (g.Z + 31) / 32;
+    const size_t smem = (size_t)warps * (NA + 2) * 4;   // per-warp staging of one row's aligned sign words
+    const bool vec = (g.Z % VN == 0) && ((reinterpret_cast<uintptr_t>(sdf) & 15) == 0) && smem <= MAX_OPTIN_SMEM;
     if (vec) {
-        const int NA = (g.Z + 31) / 32;
-        const size_t smem = (size_t)warps * (NA + 2) * 4;
         const int ctas = std::min(cdiv(g.NR, warps), sm_count() * 6);  // persistent: warps stride over the rows
         kernel_attrs(reinterpret_cast<const void *>(sign_pack_vec_kernel<T>), "DISO_CARVEOUT_SIGN", -1, smem);
-        LAUNCH(sizeof(T) == 4 ? "sign_pack_f32x4" : "sign_pack_f64x2", st, sign_pack_vec_kernel<T><<<ctas, warps * 32, smem, st>>>(sdf, g, isoT, p.S, p.counts));
+        LAUNCH(sizeof(T) == 4 ? "sign_pack_f32x4" : "sign_pack_f64x2", st, sign_pack_vec_kernel<T><<<ctas, warps * 32, smem, st>>>(sdf, g, isoT, p.S, p.counts, tf));
     } else {
-        LAUNCH("sign_pack", st, sign_pack_kernel<T><<<cdiv(g.NR, warps), warps * 32, 0, st>>>(sdf, g, isoT, p.S, p.counts));
+        LAUNCH("sign_pack", st, sign_pack_kernel<T><<<cdiv(g.NR, warps), warps * 32, 0, st>>>(sdf, g, isoT, p.S, p.counts, tf));
     }
     if (alg == DISO_ALG_MC)
         LAUNCH("classify_scan_mc", st, classify_scan_kernel<DISO_ALG_MC><<<L.n_tiles, SCAN_TILE, 0, st>>>(g, p.S, p.E, p.aux, p.C, p.active, p.desc, p.ticket, p.counts));
@@ -216,7 +231,7 @@ int count_impl(int alg, const T *sdf, const Geo &g, double iso, const StateLayou
 
 template <typename T>
 int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const int64_t *counts_host,
-                 int normalize, const Frame &fr, T *verts, long long *tris, cudaStream_t st)
+                 int normalize, const Frame &fr, T *verts, long long *tris, T *rec, cudaStream_t st)
 {
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     const EpilogueC<T> epi = make_epilogue_c<T>(g, fr, normalize);
@@ -224,8 +239,8 @@ int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const 
     kernel_attrs(reinterpret_cast<const void *>(edge_verts_kernel<T, true>), "DISO_CARVEOUT_EV", -1);
     kernel_attrs(reinterpret_cast<const void *>(edge_verts_kernel<T, false>), "DISO_CARVEOUT_EV", -1);
     if (te.ctas) {
-        if (te.list) LAUNCH("mc_emit_verts", st, (edge_verts_kernel<T, true><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, te.n_active, verts)));
-        else LAUNCH("mc_emit_verts", st, (edge_verts_kernel<T, false><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, te.n_active, verts)));
+        if (te.list) LAUNCH("mc_emit_verts", st, (edge_verts_kernel<T, true><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, te.n_active, verts, rec)));
+        else LAUNCH("mc_emit_verts", st, (edge_verts_kernel<T, false><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, te.n_active, verts, rec)));
     }
     if (tc.ctas) {
         const uint2 *F = reinterpret_cast<const uint2 *>(p.aux);
@@ -239,7 +254,7 @@ int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const 
 
 template <typename T>
 int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const int64_t *counts_host,
-                  int normalize, const Frame &fr, T *scratch, T *verts, long long *quads, cudaStream_t st)
+                  int normalize, const Frame &fr, T *scratch, T *verts, long long *quads, T *rec, cudaStream_t st)
 {
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
@@ -252,15 +267,15 @@ int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const
     kernel_attrs(reinterpret_cast<const void *>(dmc_edges2_kernel<T, 0, true>), "DISO_CARVEOUT_QUAD", -1);
     kernel_attrs(reinterpret_cast<const void *>(dmc_edges2_kernel<T, 0, false>), "DISO_CARVEOUT_QUAD", -1);
     if (te.ctas) {
-        if (te.list) LAUNCH("dmc_edge_crossings", st, (edge_verts_kernel<T, true><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch)));
-        else LAUNCH("dmc_edge_crossings", st, (edge_verts_kernel<T, false><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch)));
+        if (te.list) LAUNCH("dmc_edge_crossings", st, (edge_verts_kernel<T, true><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch, rec)));
+        else LAUNCH("dmc_edge_crossings", st, (edge_verts_kernel<T, false><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch, rec)));
     }
     if (tc.ctas) {
         if (tc.list) LAUNCH("dmc_emit_verts", st, (dmc_dual_verts_kernel<T, true><<<tc.ctas, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, tc.list, tc.n_active, verts)));
         else LAUNCH("dmc_emit_verts", st, (dmc_dual_verts_kernel<T, false><<<tc.ctas, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, tc.list, tc.n_active, verts)));
     }
     if (te.ctas) {
-#define DISO_QUADS(LISTED, OFFSET) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, LISTED, OFFSET><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, fr.id_offset, quads, nullptr)))
+#define DISO_QUADS(LISTED, OFFSET) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, LISTED, OFFSET><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, fr.id_offset, quads, nullptr, 0)))
         if (fr.id_offset != 0) { if (te.list) DISO_QUADS(true, true); else DISO_QUADS(false, true); }
         else                   { if (te.list) DISO_QUADS(true, false); else DISO_QUADS(false, false); }
 #undef DISO_QUADS
@@ -304,9 +319,41 @@ int launch_bwd_compact(const T *sdf, const T *deform, const Geo &g, T isoT, T pa
     return DISO_OK;
 }
 
+// v2 backward from saved edge records (mc_backward_v2.cuh).
+template <typename T, bool HAS_DEF, bool G_SOA, int BX, int BY>
+int launch_bwd2(const Geo &g, T isoT, T ix, T iy, T iz, const uint4 *E, const T *gsrc, const T *rec,
+                T *adj_sdf, T *adj_deform, unsigned *work, bool sparse, cudaStream_t st)
+{
+    using L = Bwd2Layout<T, HAS_DEF, BX, BY>;
+    const size_t smem = L::bytes;
+    const int ntx = cdiv(g.X, BX), nty = cdiv(g.Y, BY);
+    const long long nblk = (long long)ntx * nty * g.NC;
+    if (sparse) {
+        auto kern = mc_backward2_queue_kernel<T, HAS_DEF, G_SOA, BX, BY>;
+        kernel_attrs(reinterpret_cast<const void *>(kern), "DISO_CARVEOUT_BWD2", -1, smem);
+        const size_t G = (size_t)g.X * g.Y * g.Z;
+        if (adj_sdf) CU_TRY(cudaMemsetAsync(adj_sdf, 0, G * sizeof(T), st));
+        if (HAS_DEF && adj_deform) CU_TRY(cudaMemsetAsync(adj_deform, 0, G * 3 * sizeof(T), st));
+        CU_TRY(cudaMemsetAsync(work, 0, 64, st));
+        LAUNCH("mc_backward_mark", st, (bwd_mark_kernel<BX, BY><<<cdiv(nblk, 256), 256, 0, st>>>(g, E, ntx, nty, work)));
+        const int ctas = (int)std::min<long long>(nblk, (long long)sm_count() * 6);
+        LAUNCH("mc_backward", st, kern<<<ctas, B2_THREADS, smem, st>>>(g, isoT, ix, iy, iz, E, gsrc, rec, adj_sdf, adj_deform, nty, work));
+        return DISO_OK;
+    }
+    auto kern = mc_backward2_kernel<T, HAS_DEF, G_SOA, BX, BY>;
+    kernel_attrs(reinterpret_cast<const void *>(kern), "DISO_CARVEOUT_BWD2", -1, smem);
+    const bool flat = nty > 65535 || ntx > 65535;
+    const dim3 grid = flat ? dim3((unsigned)nblk, 1, 1) : dim3((unsigned)g.NC, (unsigned)nty, (unsigned)ntx);
+    LAUNCH("mc_backward", st, kern<<<grid, B2_THREADS, smem, st>>>(g, isoT, ix, iy, iz, E, gsrc, rec, adj_sdf, adj_deform,
+                                                                   ntx, nty, flat ? 1 : 0));
+    return DISO_OK;
+}
+
+// gsrc: per-edge adjoints, [n,3] or (g_soa) blocked SoA.  rec != NULL selects the v2 kernel.
 template <typename T>
 int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const int64_t *counts_host,
-                     const T *adj_verts, int normalize, int X_global, T *adj_sdf, T *adj_deform, cudaStream_t st)
+                     const T *gsrc, bool g_soa, const T *rec, int normalize, int X_global, T *adj_sdf, T *adj_deform,
+                     cudaStream_t st)
 {
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     // chain rule of verts / (dims - 1): multiply by the reciprocal (gradients carry a 1e-5 bar, not bit parity)
@@ -315,29 +362,44 @@ int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, co
     // sparse surface (known from the counts the caller read back in the forward): fewer than 1/8 of the chunks own a
     // crossing edge -> zero fill + touched-block list instead of one CTA per block
     static const int force = env_int("DISO_BWD_SPARSE", -1);   // experiment knob: 0 / 1 force the path
-    bool sparse = counts_host && counts_host[DISO_CNT_EDGE_CHUNKS] * 8 < (long long)g.NCH;
+    // (and the grid is large enough for its four extra launches to pay: below ~64 k chunks the dense grid is a few waves)
+    bool sparse = counts_host && counts_host[DISO_CNT_EDGE_CHUNKS] * 8 < (long long)g.NCH && g.NCH >= 65536;
     if (force >= 0) sparse = force != 0;
+    if (rec) {
+        if (deform) {
+            if (g_soa) return launch_bwd2<T, true, true, BWD2_BX, BWD2_BY>(g, isoT, ix, iy, iz, p.E, gsrc, rec, adj_sdf, adj_deform, p.bwd, sparse, st);
+            return launch_bwd2<T, true, false, BWD2_BX, BWD2_BY>(g, isoT, ix, iy, iz, p.E, gsrc, rec, adj_sdf, adj_deform, p.bwd, sparse, st);
+        }
+        if (g_soa) return launch_bwd2<T, false, true, BWD2_BX, BWD2_BY>(g, isoT, ix, iy, iz, p.E, gsrc, rec, adj_sdf, nullptr, p.bwd, sparse, st);
+        return launch_bwd2<T, false, false, BWD2_BX, BWD2_BY>(g, isoT, ix, iy, iz, p.E, gsrc, rec, adj_sdf, nullptr, p.bwd, sparse, st);
+    }
+    // no saved records (callers of the bare ABI, the diso._C shim): v1, which re-gathers sdf / deform
+    if (g_soa) return fail(DISO_E_INVALID, "internal: SoA adjoints need the saved edge records");
+    if (!adj_sdf || (deform && !adj_deform)) return fail(DISO_E_INVALID, "adj_sdf / adj_deform may only be NULL when edge_rec is given");
     // block shape (common.cuh: BWD_BX x BWD_BY) from sweeps on B200 (512^3 rand-flexi): 4x6 1.70 ms, 3x8 1.71, 4x7 / 4x8 1.73,
     // 8x4 1.76, 6x8 1.82, 2x8 1.90, 4x4 1.92
-    if (deform) return launch_bwd_compact<T, true, BWD_BX, BWD_BY>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, adj_verts, adj_sdf, adj_deform, p.bwd, sparse, st);
-    return launch_bwd_compact<T, false, BWD_BX, BWD_BY>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, adj_verts, adj_sdf, adj_deform, p.bwd, sparse, st);
+    if (deform) return launch_bwd_compact<T, true, BWD_BX, BWD_BY>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, gsrc, adj_sdf, adj_deform, p.bwd, sparse, st);
+    return launch_bwd_compact<T, false, BWD_BX, BWD_BY>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, gsrc, adj_sdf, adj_deform, p.bwd, sparse, st);
 }
 
 template <typename T>
 int dmc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const int64_t *counts_host,
-                      const T *adj_verts, int normalize, int X_global, int grad_mode, T *scratch, T *adj_sdf, T *adj_deform, cudaStream_t st)
+                      const T *adj_verts, const T *rec, int normalize, int X_global, int grad_mode, T *scratch, T *adj_sdf,
+                      T *adj_deform, cudaStream_t st)
 {
     const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
     const T ix = normalize ? T(1) / (T(X_global) - T(1)) : T(1), iy = normalize ? T(1) / (T(g.Y) - T(1)) : T(1),
             iz = normalize ? T(1) / (T(g.Z) - T(1)) : T(1);
     const TileGrid te = tile_grid(p, g, counts_host, 0);
+    // stage A writes the per-edge adjoints in blocked SoA form when stage B is the v2 kernel (coalesced on both sides)
+    const int g_soa = rec ? 1 : 0;
     if (te.ctas) {
-#define DISO_ADJ(MODE, LISTED) { kernel_attrs(reinterpret_cast<const void *>(dmc_edges2_kernel<T, MODE, LISTED>), "DISO_CARVEOUT_ADJ", -1); LAUNCH("dmc_edge_adjoint", st, (dmc_edges2_kernel<T, MODE, LISTED><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, ix, iy, iz, adj_verts, 0ll, nullptr, scratch))); }
+#define DISO_ADJ(MODE, LISTED) { kernel_attrs(reinterpret_cast<const void *>(dmc_edges2_kernel<T, MODE, LISTED>), "DISO_CARVEOUT_ADJ", -1); LAUNCH("dmc_edge_adjoint", st, (dmc_edges2_kernel<T, MODE, LISTED><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, ix, iy, iz, adj_verts, 0ll, nullptr, scratch, g_soa))); }
         if (grad_mode == DISO_GRAD_EXACT) { if (te.list) DISO_ADJ(1, true) else DISO_ADJ(1, false) }
         else                              { if (te.list) DISO_ADJ(2, true) else DISO_ADJ(2, false) }
 #undef DISO_ADJ
     }
-    return mc_backward_impl<T>(sdf, deform, g, iso, p, counts_host, scratch, 0, g.X, adj_sdf, adj_deform, st);
+    return mc_backward_impl<T>(sdf, deform, g, iso, p, counts_host, scratch, g_soa != 0, rec, 0, g.X, adj_sdf, adj_deform, st);
 }
 
 }  // namespace
@@ -416,83 +478,105 @@ int diso_b200_count(int alg, const void *sdf, int dtype, int X, int Y, int Z, do
     return count_impl<double>(alg, static_cast<const double *>(sdf), g, iso, L, p, st);
 }
 
+int diso_b200_read_counts(const void *state, int64_t *counts_host, void *stream)
+{
+    if (!state || !counts_host) return fail(DISO_E_INVALID, "null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CU_TRY(cudaMemcpyAsync(counts_host, state, DISO_COUNT_SLOTS * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return DISO_OK;
+}
+
 int diso_b200_mc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
                       const void *state, const int64_t *counts_host, int normalize, const diso_b200_frame *frame,
-                      void *verts, int64_t *tris, void *stream)
+                      void *verts, int64_t *tris, void *edge_rec, int64_t edge_rec_stride, void *stream)
 {
     int rc = check_dims(DISO_ALG_MC, dtype, X, Y, Z);
     if (rc) return rc;
     if (!sdf || !state || !verts || !tris) return fail(DISO_E_INVALID, "null pointer");
+    if (edge_rec && edge_rec_stride < 1) return fail(DISO_E_INVALID, "edge_rec_stride must be >= the number of crossing edges");
     const Geo g = make_geo(X, Y, Z);
     const Frame fr = make_frame(frame, X);
     const StatePtrs p = state_ptrs(const_cast<void *>(state), make_layout(DISO_ALG_MC, g));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == DISO_F32)
         return mc_emit_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, counts_host, normalize, fr,
-                                   static_cast<float *>(verts), reinterpret_cast<long long *>(tris), st);
+                                   static_cast<float *>(verts), reinterpret_cast<long long *>(tris), static_cast<float *>(edge_rec), st);
     return mc_emit_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, counts_host, normalize, fr,
-                                static_cast<double *>(verts), reinterpret_cast<long long *>(tris), st);
+                                static_cast<double *>(verts), reinterpret_cast<long long *>(tris), static_cast<double *>(edge_rec), st);
 }
 
 int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
                        const void *state, const int64_t *counts_host, int normalize, const diso_b200_frame *frame,
-                       void *scratch, void *verts, int64_t *quads, void *stream)
+                       void *scratch, void *verts, int64_t *quads, void *edge_rec, int64_t edge_rec_stride, void *stream)
 {
     int rc = check_dims(DISO_ALG_DMC, dtype, X, Y, Z);
     if (rc) return rc;
     if (!sdf || !state || !scratch || !verts || !quads) return fail(DISO_E_INVALID, "null pointer");
+    if (edge_rec && edge_rec_stride < 1) return fail(DISO_E_INVALID, "edge_rec_stride must be >= the number of crossing edges");
     const Geo g = make_geo(X, Y, Z);
     const Frame fr = make_frame(frame, X);
     const StatePtrs p = state_ptrs(const_cast<void *>(state), make_layout(DISO_ALG_DMC, g));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == DISO_F32)
         return dmc_emit_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, counts_host, normalize, fr,
-                                    static_cast<float *>(scratch), static_cast<float *>(verts), reinterpret_cast<long long *>(quads), st);
+                                    static_cast<float *>(scratch), static_cast<float *>(verts), reinterpret_cast<long long *>(quads), static_cast<float *>(edge_rec), st);
     return dmc_emit_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, counts_host, normalize, fr,
-                                 static_cast<double *>(scratch), static_cast<double *>(verts), reinterpret_cast<long long *>(quads), st);
+                                 static_cast<double *>(scratch), static_cast<double *>(verts), reinterpret_cast<long long *>(quads), static_cast<double *>(edge_rec), st);
 }
 
 int diso_b200_mc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
                           void *state, const int64_t *counts_host, const void *adj_verts, int normalize,
-                          const diso_b200_frame *frame, void *adj_sdf, void *adj_deform, void *stream)
+                          const diso_b200_frame *frame, const void *edge_rec, int64_t edge_rec_stride, void *adj_sdf,
+                          void *adj_deform, void *stream)
 {
     int rc = check_dims(DISO_ALG_MC, dtype, X, Y, Z);
     if (rc) return rc;
-    if (!sdf || !state || !adj_verts || !adj_sdf) return fail(DISO_E_INVALID, "null pointer");
-    if ((deform == nullptr) != (adj_deform == nullptr)) return fail(DISO_E_INVALID, "deform and adj_deform must both be given or both be NULL");
+    if (!sdf || !state || !adj_verts) return fail(DISO_E_INVALID, "null pointer");
+    if (!deform && adj_deform) return fail(DISO_E_INVALID, "adj_deform given without deform");
+    if (!edge_rec && (!adj_sdf || (deform != nullptr) != (adj_deform != nullptr)))
+        return fail(DISO_E_INVALID, "without edge_rec, adj_sdf is required and adj_deform must be given iff deform is");
+    if (edge_rec && edge_rec_stride < 1) return fail(DISO_E_INVALID, "edge_rec_stride must be >= the number of crossing edges");
+    if (!adj_sdf && !adj_deform) return DISO_OK;   // nothing to compute
     const Geo g = make_geo(X, Y, Z);
     const Frame fr = make_frame(frame, X);
     const StatePtrs p = state_ptrs(state, make_layout(DISO_ALG_MC, g));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == DISO_F32)
         return mc_backward_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, counts_host,
-                                       static_cast<const float *>(adj_verts), normalize, fr.X_global, static_cast<float *>(adj_sdf),
-                                       static_cast<float *>(adj_deform), st);
+                                       static_cast<const float *>(adj_verts), false, static_cast<const float *>(edge_rec),
+                                       normalize, fr.X_global, static_cast<float *>(adj_sdf), static_cast<float *>(adj_deform), st);
     return mc_backward_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, counts_host,
-                                    static_cast<const double *>(adj_verts), normalize, fr.X_global, static_cast<double *>(adj_sdf),
-                                    static_cast<double *>(adj_deform), st);
+                                    static_cast<const double *>(adj_verts), false, static_cast<const double *>(edge_rec),
+                                    normalize, fr.X_global, static_cast<double *>(adj_sdf), static_cast<double *>(adj_deform), st);
 }
 
 int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
                            void *state, const int64_t *counts_host, const void *adj_verts, int normalize,
-                           const diso_b200_frame *frame, int grad_mode, void *scratch, void *adj_sdf, void *adj_deform,
-                           void *stream)
+                           const diso_b200_frame *frame, int grad_mode, const void *edge_rec, int64_t edge_rec_stride,
+                           void *scratch, void *adj_sdf, void *adj_deform, void *stream)
 {
     int rc = check_dims(DISO_ALG_DMC, dtype, X, Y, Z);
     if (rc) return rc;
-    if (!sdf || !state || !adj_verts || !adj_sdf || !scratch) return fail(DISO_E_INVALID, "null pointer");
-    if ((deform == nullptr) != (adj_deform == nullptr)) return fail(DISO_E_INVALID, "deform and adj_deform must both be given or both be NULL");
+    if (!sdf || !state || !adj_verts || !scratch) return fail(DISO_E_INVALID, "null pointer");
+    if (!deform && adj_deform) return fail(DISO_E_INVALID, "adj_deform given without deform");
+    if (!edge_rec && (!adj_sdf || (deform != nullptr) != (adj_deform != nullptr)))
+        return fail(DISO_E_INVALID, "without edge_rec, adj_sdf is required and adj_deform must be given iff deform is");
+    if (edge_rec && edge_rec_stride < 1) return fail(DISO_E_INVALID, "edge_rec_stride must be >= the number of crossing edges");
     if (grad_mode != DISO_GRAD_REFERENCE && grad_mode != DISO_GRAD_EXACT) return fail(DISO_E_INVALID, "unknown grad_mode %d", grad_mode);
+    if (!adj_sdf && !adj_deform) return DISO_OK;
     const Geo g = make_geo(X, Y, Z);
     const Frame fr = make_frame(frame, X);
     const StatePtrs p = state_ptrs(state, make_layout(DISO_ALG_DMC, g));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == DISO_F32)
         return dmc_backward_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, counts_host,
-                                        static_cast<const float *>(adj_verts), normalize, fr.X_global, grad_mode, static_cast<float *>(scratch),
+                                        static_cast<const float *>(adj_verts), static_cast<const float *>(edge_rec),
+                                        normalize, fr.X_global, grad_mode, static_cast<float *>(scratch),
                                         static_cast<float *>(adj_sdf), static_cast<float *>(adj_deform), st);
     return dmc_backward_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, counts_host,
-                                     static_cast<const double *>(adj_verts), normalize, fr.X_global, grad_mode, static_cast<double *>(scratch),
+                                     static_cast<const double *>(adj_verts), static_cast<const double *>(edge_rec),
+                                     normalize, fr.X_global, grad_mode, static_cast<double *>(scratch),
                                      static_cast<double *>(adj_sdf), static_cast<double *>(adj_deform), st);
 }
 

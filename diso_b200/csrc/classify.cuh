@@ -17,14 +17,31 @@
 
 namespace diso {
 
+// Tails of the state arrays that no kernel computes (sign words beyond the last chunk read as "inside", records
+// beyond it as "no edges"): filled by the sign pass itself instead of three cudaMemsetAsync calls per extraction
+// (host latency is what a 64^3 call is made of).  classify_scan, the first reader, runs after this kernel.
+struct TailFill {
+    unsigned *s_tail; int n_s;      // sign words  := ~0
+    uint4 *e_tail; int n_e;         // edge records := 0
+    uint2 *aux_tail; int n_aux;     // F / P records (8-byte units) := 0
+};
+__device__ __forceinline__ void fill_tails(const TailFill &tf)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int i = t; i < tf.n_s; i += nt) tf.s_tail[i] = FULL;
+    for (int i = t; i < tf.n_e; i += nt) tf.e_tail[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = t; i < tf.n_aux; i += nt) tf.aux_tail[i] = make_uint2(0u, 0u);
+}
+
 // ------------------------------------------------------------------------------------------
 // K1: one warp per padded z-row.  Lane j of iteration c looks at padded point zp = 32c + j.
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) sign_pack_kernel(const T *__restrict__ sdf, Geo g, T iso,
                                                         unsigned *__restrict__ S,
-                                                        long long *__restrict__ counts)
+                                                        long long *__restrict__ counts, TailFill tf)
 {
+    fill_tails(tf);
     const int lane = threadIdx.x & 31;
     const int warps_per_cta = blockDim.x >> 5;
     const int row = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
@@ -86,8 +103,9 @@ template <> struct Vec128<double> {
 
 template <typename T>
 __global__ void __launch_bounds__(256) sign_pack_vec_kernel(const T *__restrict__ sdf, Geo g, T iso, unsigned *__restrict__ S,
-                                                            long long *__restrict__ counts)
+                                                            long long *__restrict__ counts, TailFill tf)
 {
+    fill_tails(tf);
     using VT = Vec128<T>;
     using V = typename VT::type;
     constexpr int N = VT::N;        // values per lane per load

@@ -71,6 +71,11 @@ constexpr int SCAN_TILE = 256;  // chunks per scan tile == threads per classify 
 #define DISO_BWD_BY 6
 #endif
 constexpr int BWD_BX = DISO_BWD_BX, BWD_BY = DISO_BWD_BY;  // rows per backward block (x, y); one 32-point chunk in z
+#ifndef DISO_BWD2_BX
+#define DISO_BWD2_BX 4
+#define DISO_BWD2_BY 6
+#endif
+constexpr int BWD2_BX = DISO_BWD2_BX, BWD2_BY = DISO_BWD2_BY;  // same for the saved-record backward (mc_backward_v2.cuh)
 
 // Byte offsets of the arrays inside the caller-owned state buffer.
 struct StateLayout {
@@ -118,7 +123,9 @@ inline StateLayout make_layout(int alg, const Geo &g)
     o += (size_t)g.NCH * 2 * 4;
     o = align_up(o, 256);
     L.off_bwd = o;
-    o += ((size_t)((g.X + BWD_BX - 1) / BWD_BX) * ((g.Y + BWD_BY - 1) / BWD_BY) * g.NC + 16) * 4;
+    const size_t blocks1 = (size_t)((g.X + BWD_BX - 1) / BWD_BX) * ((g.Y + BWD_BY - 1) / BWD_BY) * g.NC;
+    const size_t blocks2 = (size_t)((g.X + BWD2_BX - 1) / BWD2_BX) * ((g.Y + BWD2_BY - 1) / BWD2_BY) * g.NC;
+    o += ((blocks1 > blocks2 ? blocks1 : blocks2) + 16) * 4;
     L.total = align_up(o, 256);
     return L;
 }

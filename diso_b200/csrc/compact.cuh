@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(CT_THREADS) edge_verts_kernel(const T *__restr
                                                               Geo g, T iso, T padv, EpilogueC<T> epi,
                                                               const uint4 *__restrict__ E,
                                                               const unsigned *__restrict__ alist, int n_active,
-                                                              T *__restrict__ verts)
+                                                              T *__restrict__ verts, T *__restrict__ rec)
 {
     __shared__ unsigned short s_list[CT_MAX_EDGES];
     __shared__ TilePos s_pos[CT_CHUNKS];
@@ -190,13 +190,22 @@ __global__ void __launch_bounds__(CT_THREADS) edge_verts_kernel(const T *__restr
                 p1.x = p1.x + __ldg(f); p1.y = p1.y + __ldg(f + 1); p1.z = p1.z + __ldg(f + 2);
             }
         }
+        const Vec3<T> dp{p1.x - p0.x, p1.y - p0.y, p1.z - p0.z};
         Vec3<T> p;
-        p.x = fma_rn(p1.x - p0.x, t, p0.x);
-        p.y = fma_rn(p1.y - p0.y, t, p0.y);
-        p.z = fma_rn(p1.z - p0.z, t, p0.z);
+        p.x = fma_rn(dp.x, t, p0.x);
+        p.y = fma_rn(dp.y, t, p0.y);
+        p.z = fma_rn(dp.z, t, p0.z);
         p = epi.apply(p);
-        T *dst = verts + (size_t)(tile_base + i) * 3;
+        const size_t rank = (size_t)tile_base + i;
+        T *dst = verts + rank * 3;
         st_stream(dst, p.x); st_stream(dst + 1, p.y); st_stream(dst + 2, p.z);
+        if (rec) {
+            // saved for the backward (mc_backward_v2.cuh): everything adjComputeMcVert (cumc.cu:412-453) needs of this
+            // edge, as five arrays indexed by rank -- coalesced here and there, no sdf / deform gathers in the backward
+            // (groups of 32 edges, component-major inside a group: mc_backward_v2.cuh:blk_index)
+            T *r = rec + (rank >> 5) * 160 + (rank & 31);
+            r[0] = dp.x; r[32] = dp.y; r[64] = dp.z; r[96] = d0; r[128] = d1;
+        }
     }
 }
 

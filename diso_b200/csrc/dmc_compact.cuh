@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
                                                               const unsigned short *__restrict__ C,
                                                               const unsigned *__restrict__ alist, int n_active, T ix, T iy, T iz,
                                                               const T *__restrict__ adj_dual, long long id_offset,
-                                                              long long *__restrict__ quads, T *__restrict__ gedge)
+                                                              long long *__restrict__ quads, T *__restrict__ gedge, int gedge_soa)
 {
     __shared__ unsigned short s_list[CT_MAX_EDGES];
     __shared__ unsigned s_case[256];
@@ -80,8 +80,13 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
             __stcs(dst, make_longlong2(id[0], id[1]));
             __stcs(dst + 1, make_longlong2(id[2], id[3]));
         } else {
-            T *dst = gedge + rank * 3;
-            dst[0] = acc.x * ix; dst[1] = acc.y * iy; dst[2] = acc.z * iz;
+            if (gedge_soa) {   // blocked SoA (mc_backward_v2.cuh:blk_index): coalesced here and in stage B
+                T *dst = gedge + (rank >> 5) * 96 + (rank & 31);
+                dst[0] = acc.x * ix; dst[32] = acc.y * iy; dst[64] = acc.z * iz;
+            } else {
+                T *dst = gedge + rank * 3;
+                dst[0] = acc.x * ix; dst[1] = acc.y * iy; dst[2] = acc.z * iz;
+            }
         }
     }
 }

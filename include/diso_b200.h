@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DISO_B200_ABI_VERSION 2
+#define DISO_B200_ABI_VERSION 3
 
 #define DISO_ALG_MC 0
 #define DISO_ALG_DMC 1
@@ -96,24 +96,39 @@ int diso_b200_state_layout(int alg, int X, int Y, int Z, int64_t *out);
 int diso_b200_count(int alg, const void *sdf, int dtype, int X, int Y, int Z, double iso,
                     void *state, size_t state_bytes, void *stream);
 
+/* The forward's single host synchronisation: copies the DISO_COUNT_SLOTS int64 at the start of `state` into
+ * counts_host (HOST memory; pinned memory avoids a staging copy) on `stream` and waits for that stream.
+ * (The reference synchronises five times per forward: cumc.cu:674,694,723 and the two reductions of
+ * diso/__init__.py:49.) */
+int diso_b200_read_counts(const void *state, int64_t *counts_host, void *stream);
+
 /* Phase 2, marching cubes (replaces create_cell_mc_verts / create_cell_mc_tris,
  * cumc.cu:370-410, 564-612, and the epilogue diso/__init__.py:56-61).
  * verts: [n_verts,3] dtype; tris: [n_tris,3] int64.  deform may be NULL.
  * counts_host: HOST pointer to the DISO_COUNT_SLOTS int64 the caller read back after
  * diso_b200_count (the active-chunk counts size the launches; sparse surfaces then cost time
- * proportional to the surface, not the volume).  NULL = visit every chunk. */
+ * proportional to the surface, not the volume).  NULL = visit every chunk.
+ *
+ * edge_rec (ABI v3, may be NULL): caller-owned, 5 * 32 * ceil(edge_rec_stride / 32) elements of dtype with
+ * edge_rec_stride >= #crossing edges (groups of 32 edges, component-major inside a group).  When given, the edge pass also SAVES, per crossing edge and indexed by its rank (== its MC vertex id ==
+ * its DMC quad id), what the adjoint of computeMcVert needs (adjComputeMcVert, cumc.cu:412-453): p1 - p0 (x, y, z),
+ * d0, d1.  Passing the same buffer to *_backward selects the saved-record backward, which reads neither sdf nor
+ * deform; the reference instead re-runs the whole forward inside backward
+ * (diso/__init__.py:32,86).  20 (fp32) / 40 (fp64) bytes per crossing edge; callers that never differentiate pass NULL. */
 int diso_b200_mc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
                       double iso, const void *state, const int64_t *counts_host, int normalize,
-                      const diso_b200_frame *frame, void *verts, int64_t *tris, void *stream);
+                      const diso_b200_frame *frame, void *verts, int64_t *tris, void *edge_rec,
+                      int64_t edge_rec_stride, void *stream);
 
 /* Phase 2, dual marching cubes (replaces create_dmc_verts / create_quads,
  * cudualmc.cu:907-955, 1027-1056, and diso/__init__.py:110-116).
  * verts: [n_verts,3] dtype; quads: [n_quads,4] int64.
- * scratch: caller-owned, n_quads*3 elements of dtype (edge crossings, each evaluated once). */
+ * scratch: caller-owned, n_quads*3 elements of dtype (edge crossings, each evaluated once).
+ * edge_rec / edge_rec_stride: as for diso_b200_mc_emit (the crossing edges are the quads). */
 int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
                        double iso, const void *state, const int64_t *counts_host, int normalize,
                        const diso_b200_frame *frame, void *scratch, void *verts, int64_t *quads,
-                       void *stream);
+                       void *edge_rec, int64_t edge_rec_stride, void *stream);
 
 /* Backward, marching cubes (replaces adj_create_cell_mc_verts, cumc.cu:474-512, the dense
  * zero-fills of diso/__init__.py:33,40 and the pad-backward slices).  adj_verts is dL/dverts in
@@ -122,18 +137,24 @@ int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, in
  * accumulation is an atomic-free gather in a fixed order, so results are deterministic.
  * counts_host: as for emit (NULL allowed); on sparse surfaces it selects the zero-fill + touched-block
  * path, which uses a small work area inside `state` (hence not const: do not run two backward
- * passes on the SAME state concurrently on different streams). */
+ * passes on the SAME state concurrently on different streams).
+ * edge_rec (ABI v3): the buffer the emit call filled, or NULL.  With it the adjoint runs from the saved records
+ * (mc_backward_v2.cuh) and either of adj_sdf / adj_deform may be NULL when that gradient is not wanted; without it
+ * the kernel re-gathers sdf / deform (mc_backward_compact.cuh) and both outputs are required. */
 int diso_b200_mc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
                           double iso, void *state, const int64_t *counts_host, const void *adj_verts,
-                          int normalize, const diso_b200_frame *frame, void *adj_sdf, void *adj_deform,
-                          void *stream);
+                          int normalize, const diso_b200_frame *frame, const void *edge_rec,
+                          int64_t edge_rec_stride, void *adj_sdf, void *adj_deform, void *stream);
 
 /* Backward, dual marching cubes (replaces adj_create_dmc_verts, cudualmc.cu:957-1005).
- * scratch: caller-owned, n_quads*3 elements of dtype (per-edge adjoints). */
+ * scratch: caller-owned per-edge adjoints: n_quads*3 elements of dtype, or 3 * 32 * ceil(n_quads / 32) when
+ * edge_rec is given (groups of 32 edges, like the records).
+ * edge_rec / edge_rec_stride: as for diso_b200_mc_backward. */
 int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
                            double iso, void *state, const int64_t *counts_host,
                            const void *adj_verts, int normalize, const diso_b200_frame *frame,
-                           int grad_mode, void *scratch, void *adj_sdf, void *adj_deform, void *stream);
+                           int grad_mode, const void *edge_rec, int64_t edge_rec_stride, void *scratch,
+                           void *adj_sdf, void *adj_deform, void *stream);
 
 /* Quad -> triangle split of diso/__init__.py:118-147 as two kernels (no PyTorch
  * temporaries).  verts [n_verts,3] dtype (API frame), quads [n_quads,4] int64, faces

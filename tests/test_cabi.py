@@ -48,7 +48,7 @@ def test_library_has_sm100a_code_and_no_torch_dependency():
 
 
 def test_abi_version_and_state_bytes(lib):
-    assert lib.diso_b200_abi_version() == 2
+    assert lib.diso_b200_abi_version() == 3
     for alg in (0, 1):
         small = lib.diso_b200_state_bytes(alg, 8, 8, 8)
         big = lib.diso_b200_state_bytes(alg, 512, 512, 512)
@@ -72,5 +72,8 @@ def test_argument_errors_return_codes(lib):
     rc = lib.diso_b200_count(0, ctypes.c_void_p(256), 0, 2000, 2000, 2000, 0.0, ctypes.c_void_p(256), 1 << 40, None)
     assert rc == -4  # too large for one call
     rc = lib.diso_b200_mc_backward(ctypes.c_void_p(256), ctypes.c_void_p(256), 0, 4, 4, 4, 0.0, ctypes.c_void_p(256), None,
-                                   ctypes.c_void_p(256), 1, None, ctypes.c_void_p(256), None, None)
-    assert rc == -1  # deform without adj_deform
+                                   ctypes.c_void_p(256), 1, None, None, 0, ctypes.c_void_p(256), None, None)
+    assert rc == -1  # no saved edge records: deform without adj_deform is an error
+    rc = lib.diso_b200_mc_backward(ctypes.c_void_p(256), None, 0, 4, 4, 4, 0.0, ctypes.c_void_p(256), None,
+                                   ctypes.c_void_p(256), 1, None, ctypes.c_void_p(256), 0, ctypes.c_void_p(256), None, None)
+    assert rc == -1 and b"edge_rec_stride" in lib.diso_b200_last_error()
