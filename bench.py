@@ -36,6 +36,61 @@ METRIC = "Gvoxels/s fwd+bwd DiffMC+DiffDMC 512^3 rand SDF"
 UNIT = "Gvoxel/s"
 
 
+def load_reference():
+    """The UNMODIFIED reference build (baseline/_ref, installed by __graft_entry__.build()) under the alias
+    ``diso_ref``; None when it is not in the snapshot."""
+    import importlib.util
+    if "diso_ref" in sys.modules:
+        return sys.modules["diso_ref"]
+    pkg = os.path.join(ROOT, "baseline", "_ref", "diso")
+    if not os.path.exists(os.path.join(pkg, "_C.so")):
+        return None
+    try:
+        spec = importlib.util.spec_from_file_location("diso_ref", os.path.join(pkg, "__init__.py"), submodule_search_locations=[pkg])
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["diso_ref"] = mod
+        spec.loader.exec_module(mod)
+        return mod
+    except Exception:
+        sys.modules.pop("diso_ref", None)
+        return None
+
+
+def bind_to_gpu_numa_node(local_rank, world):
+    """Pin this process to the host cores of its GPU's NUMA node BEFORE pinned buffers are allocated (first touch
+    places them on that node).  Falls back to an even split of the visible cores.  Returns a description."""
+    try:
+        import torch
+        cpus_all = sorted(os.sched_getaffinity(0))
+        node = None
+        try:
+            prop = torch.cuda.get_device_properties(local_rank)
+            bus = "%04x:%02x:%02x.0" % (getattr(prop, "pci_domain_id", 0), prop.pci_bus_id, prop.pci_device_id)
+            with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+                node = int(f.read().strip())
+        except Exception:
+            node = None
+        cpus = None
+        if node is not None and node >= 0:
+            with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+                cpus = set()
+                for part in f.read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus = sorted(cpus & set(cpus_all)) or None
+        how = "numa node %s" % node
+        if cpus is None:
+            if world <= 1:
+                return "unbound (single rank)"
+            per = max(1, len(cpus_all) // world)
+            cpus = cpus_all[local_rank * per: (local_rank + 1) * per] or cpus_all
+            how = "even split (no NUMA information)"
+        os.sched_setaffinity(0, cpus)
+        return "%s: %d cores" % (how, len(cpus))
+    except Exception as ex:
+        return "unbound (%s)" % type(ex).__name__
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -199,6 +254,98 @@ def run_reference_cpu_arm(args, rank, world, why=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# C5b: ONE large grid in slabs along dim 0 (diso_b200/parallel.py), timed inside the N > 1 runs
+# ------------------------------------------------------------------------------------------------
+def _slab_layers(dev, n, xa, xb):
+    """Layers [xa, xb) of the n^3 rand-flexi grid + deform, generated on the device from per-layer seeds (no rank ever
+    holds the whole grid; the unsharded comparison on rank 0 generates all layers the same way)."""
+    import torch
+
+    def layer(x, shape):
+        g = torch.Generator(device=dev).manual_seed(1000003 * x + 17)
+        return torch.rand(shape, generator=g, device=dev)
+    sdf = torch.stack([layer(x, (n, n)) - 0.1 for x in range(xa, xb)])
+    deform = torch.stack([0.5 * torch.tanh(layer(x + n, (n, n, 3))) for x in range(xa, xb)])
+    return sdf, deform
+
+
+def run_slab_leg(rank, world, dev, n=1024, steps=3, warmup=2):
+    """DiffMC + DiffDMC fwd+bwd of one n^3 grid sharded over the ranks: halo P2P + count all_gather over NCCL, ids and
+    vertices stitched by the kernels (frame).  Then rank 0 alone runs the SAME grid unsharded (single call per extractor).
+    Returns (on rank 0) the dict attached to the bench line as "slab"."""
+    import torch
+    import torch.distributed as dist
+    import diso_b200
+    from diso_b200 import parallel
+    xa, xb = parallel.plan_slabs(n, world)[rank]
+    sdf, deform = _slab_layers(dev, n, xa, xb)
+    sf, df = parallel.SlabField(sdf, rank, world), parallel.SlabField(deform, rank, world)
+    del sdf, deform
+    sf.ext.requires_grad_(True)
+    df.ext.requires_grad_(True)
+    mesh = {}
+
+    def step():
+        for alg in ("mc", "dmc"):
+            sf.ext.grad = df.ext.grad = None
+            verts, faces, info = parallel.extract_slab_ext(alg, sf, df, (xa, xb), n, 0.0, True)
+            (verts * 0.5).sum().backward()
+            mesh[alg] = dict(verts=info["n_verts_total"], faces=info["n_faces_total"])
+            del verts, faces
+
+    def sync():
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    for _ in range(warmup):
+        step()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    sync()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    del sf, df
+    torch.cuda.empty_cache()
+    out = {"workload": "C5b: one %d^3 grid (rand-flexi + deform, fp32) in %d slabs along dim 0, DiffMC + DiffDMC(quads) fwd+bwd per step; "
+                       "2-layer halo P2P + count all_gather over NCCL, global ids / global-frame vertices written by the kernels" % (n, world),
+           "n_gpus": world, "ms_per_step": ms, "value": 2 * n ** 3 / (ms * 1e-3) / 1e9, "unit": UNIT, "steps": steps, "warmup": warmup, "mesh": mesh}
+    # the same grid, unsharded, on rank 0 alone (the other ranks wait at the barrier)
+    if rank == 0:
+        try:
+            sdf, deform = _slab_layers(dev, n, 0, n)
+            sdf.requires_grad_(True)
+            deform.requires_grad_(True)
+            mods = ((diso_b200.DiffMC(), {}), (diso_b200.DiffDMC(), dict(return_quads=True)))
+
+            def ustep():
+                for m, kw in mods:
+                    sdf.grad = deform.grad = None
+                    v, f = m(sdf, deform, **kw)
+                    (v * 0.5).sum().backward()
+                    del v, f
+            ustep()
+            torch.cuda.synchronize()
+            u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            u0.record()
+            for _ in range(2):
+                ustep()
+            u1.record()
+            torch.cuda.synchronize()
+            ums = u0.elapsed_time(u1) / 2
+            out.update(unsharded_ms_per_step=ums, speedup_vs_unsharded=ums / ms, strong_eff_vs_unsharded=ums / ms / world)
+            del sdf, deform
+        except Exception as ex:   # e.g. not enough memory for the whole grid on one GPU
+            out["unsharded_ms_per_step"] = None
+            out["unsharded_error"] = "%s: %s" % (type(ex).__name__, str(ex)[:200])
+        torch.cuda.empty_cache()
+    dist.barrier()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def main():
@@ -215,7 +362,6 @@ def main():
         why = None
         try:
             import torch
-            from tests.refload import load_reference
             ref_mod = load_reference()
             if ref_mod is None:
                 why = "baseline/_ref not loadable"
@@ -236,6 +382,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = bind_to_gpu_numa_node(local_rank, world)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     dt = torch.float32 if args.dtype == "f32" else torch.float64
@@ -366,6 +513,41 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item()) / e2e_steps
+    del bufs
+
+    # ---- DiffDMC's DEFAULT path (return_quads=False: the quad -> triangle split of diso/__init__.py:117-147) ------
+    m_dmc = mods["dmc"][0]
+
+    def dmc_default_step():
+        sdf_d.grad = None
+        def_d.grad = None
+        v, f = m_dmc(sdf_d, def_d)
+        (v * wts["dmc"]).sum().backward()
+    for _ in range(2):
+        dmc_default_step()
+    sync_all()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nd = max(3, min(args.steps, 5))
+    d0.record()
+    for _ in range(nd):
+        dmc_default_step()
+    d1.record()
+    sync_all()
+    t = torch.tensor([d0.elapsed_time(d1) / nd], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dmc_default_ms = float(t.item())
+
+    # ---- C5b inside the multi-GPU runs: one 1024^3 grid in slabs (our arm only: the reference has no multi-GPU path) --
+    slab = None
+    if world > 1 and not is_ref and args.size >= 512 and not os.environ.get("DISO_BENCH_NO_SLAB"):
+        del sdf_d, def_d
+        wts.clear()
+        torch.cuda.empty_cache()
+        try:
+            slab = run_slab_leg(rank, world, dev)
+        except Exception as ex:
+            slab = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:300])}
 
     if rank != 0:
         if world > 1:
@@ -410,6 +592,10 @@ def main():
         "e2e": {"value": world * 2 * G / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(sdf_h.numel() * s_bytes + def_h.numel() * s_bytes), "d2h_bytes_per_step": 2 * s_bytes},
         "gpu_launches": launches,
+        "dmc_default": {"what": "DiffDMC fwd+bwd through the DEFAULT call (return_quads=False: triangles)", "ms_per_step": dmc_default_ms,
+                        "value": world * G / (dmc_default_ms * 1e-3) / 1e9, "unit": UNIT},
+        "slab": slab,
+        "host": {"affinity": affinity, "h2d_GBps_per_rank": (sdf_h.numel() + def_h.numel()) * s_bytes / (e2e_ms * 1e-3) / 1e9},
         "roofline": roofline,
         "step_roofline": {"alg_bytes_per_step": step_bytes, "achieved_GBps": step_bytes / (ms_step * 1e-3) / 1e9,
                           "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
@@ -439,7 +625,6 @@ def main():
     # ---- reference CUDA build on the same GPU, same harness (reported beside ours; N=1 only) ------
     if world == 1 and not args.no_ref_cuda and not is_ref:
         try:
-            from tests.refload import load_reference
             ref = load_reference()
             if ref is None:
                 line["ref_cuda"] = {"unavailable": "baseline/_ref not present"}
@@ -463,6 +648,24 @@ def main():
                 r1.record()
                 torch.cuda.synchronize()
                 rms = r0.elapsed_time(r1) / nref
+                rd = rmods["dmc"][0]
+
+                def rdefault():
+                    sdf_d.grad = None
+                    def_d.grad = None
+                    v, f = rd(sdf_d, def_d)
+                    (v * wts["dmc"]).sum().backward()
+                rdefault()
+                torch.cuda.synchronize()
+                r2, r3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r2.record()
+                for _ in range(2):
+                    rdefault()
+                r3.record()
+                torch.cuda.synchronize()
+                rdms = r2.elapsed_time(r3) / 2
+                line["dmc_default"]["reference_ms_per_step"] = rdms
+                line["dmc_default"]["speedup_device"] = rdms / dmc_default_ms
                 line["ref_cuda"] = {"ms_per_step": rms, "value": 2 * G / (rms * 1e-3) / 1e9, "unit": UNIT,
                                     "speedup_device": rms / ms_step,
                                     "what": "unmodified SarahWeiii/diso v0.1.4 built for sm_100 (baseline/_ref), same inputs/harness"}

@@ -7,6 +7,7 @@ Drop-in for the reference package ``diso`` (``from diso_b200 import DiffMC, Diff
 Host code is Python/PyTorch (tensor allocation, autograd plumbing, streams); all computation is
 in hand-written sm_100a CUDA kernels behind the C ABI of ``include/diso_b200.h``.
 """
+import contextlib
 import ctypes
 
 import torch
@@ -28,6 +29,31 @@ def _ptr(t):
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+_NULL = contextlib.nullcontext()
+
+
+def _on(device):
+    """Context making `device` current -- a no-op object when it already is (torch.cuda.device costs ~5 us a time,
+    which is what a 64^3 extraction is made of)."""
+    return _NULL if device.index == torch.cuda.current_device() else torch.cuda.device(device)
+
+
+_state_bytes_cache = {}
+
+
+def _state_bytes(alg, X, Y, Z):
+    key = (alg, X, Y, Z)
+    n = _state_bytes_cache.get(key)
+    if n is None:
+        L = _lib.load()
+        n = L.diso_b200_state_bytes(alg, X, Y, Z)
+        if n == 0:
+            _lib.check(-1 if not L.diso_b200_last_error() else -4)
+        if len(_state_bytes_cache) < 4096:
+            _state_bytes_cache[key] = n
+    return n
 
 
 def _blocks32(n):
@@ -71,9 +97,7 @@ def _count(alg, grid, isovalue):
     """Phase 1 + the forward's single host sync.  Returns (state tensor, counts list)."""
     L = _lib.load()
     X, Y, Z = grid.shape
-    nbytes = L.diso_b200_state_bytes(alg, X, Y, Z)
-    if nbytes == 0:
-        _lib.check(-1 if not L.diso_b200_last_error() else -4)
+    nbytes = _state_bytes(alg, X, Y, Z)
     state = torch.empty(nbytes, dtype=torch.uint8, device=grid.device)
     st = _stream()
     _lib.check(L.diso_b200_count(alg, grid.data_ptr(), _DTYPES[grid.dtype], X, Y, Z, float(isovalue),
@@ -142,7 +166,7 @@ class _Extract(Function):
         # the reference requires a contiguous adj_verts and raises otherwise (pybind.cpp:142);
         # expanded gradients (e.g. from verts.sum() with normalize=False) are made contiguous here.
         adj_verts = adj_verts.contiguous()
-        with torch.cuda.device(grid.device):
+        with _on(grid.device):
             # fully written by the kernel, zeros included; an input that needs no gradient gets no buffer at all
             # (the saved-record backward skips that output; without records both are required by the ABI)
             want_grid = need_grid or rec is None
@@ -169,7 +193,7 @@ class _Extract(Function):
 def _run(alg, dtype, grad_mode, grid, deform, isovalue, normalize, want_state=False, slab_mode=False):
     _check_inputs(grid, deform, dtype)
     k = 3 if alg == _lib.ALG_MC else 4
-    with torch.cuda.device(grid.device):
+    with _on(grid.device):
         g = grid.contiguous()
         d = deform.contiguous() if deform is not None else None
         with torch.no_grad():

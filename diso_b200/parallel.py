@@ -139,22 +139,42 @@ def _gather_counts(mine, group, world):
     return torch.stack(gathered).cpu()
 
 
-def _extract_slab_fused(alg, sdf_own, deform_own, a, b, X, isovalue, normalize, group, rank, world, grad_mode="reference"):
-    """The product path of :func:`extract_slab`: count -> exchange the per-rank totals -> emit with a
-    frame (include/diso_b200.h: diso_b200_frame), so the kernels write global-frame vertices (bit-identical
-    to a single extraction of the whole grid) and global vertex ids directly; what a rank owns are
+_idx_cache = {}
+
+
+def _prefix_index(alg_id, shape, lA, lB, device):
+    """int32-word indices (into the state buffer) of the four per-layer prefix values a rank needs:
+    E[lA].base, E[lB].base, aux[lA].base, aux[lB].base (diso_b200_state_layout)."""
+    import ctypes
+    from diso_b200 import _lib
+    key = (alg_id, tuple(shape), lA, lB, str(device))
+    idx = _idx_cache.get(key)
+    if idx is None:
+        L = _lib.load()
+        lay = (ctypes.c_int64 * 8)()
+        _lib.check(L.diso_b200_state_layout(alg_id, shape[0], shape[1], shape[2], lay))
+        off_e, off_aux, sx = lay[1], lay[2], lay[7]
+        aw = 2 if alg_id == _lib.ALG_MC else 4      # words per F / P record
+        idx = torch.tensor([off_e // 4 + lA * sx * 4, off_e // 4 + lB * sx * 4,
+                            off_aux // 4 + lA * sx * aw, off_aux // 4 + lB * sx * aw], dtype=torch.int64, device=device)
+        if len(_idx_cache) < 256:
+            _idx_cache[key] = idx
+    return idx
+
+
+def _extract_ext(alg, sdf_ext, def_ext, a, b, X, isovalue, normalize, group, rank, world, grad_mode="reference"):
+    """The product path: `sdf_ext` / `def_ext` are the slab EXTENDED by its halo layers (already exchanged).
+    count -> ONE host read (own counts, the four per-layer prefixes and every rank's totals, gathered on the device)
+    -> emit with a frame (include/diso_b200.h: diso_b200_frame), so the kernels write global-frame vertices
+    (bit-identical to a single extraction of the whole grid) and global vertex ids directly; what a rank owns are
     contiguous slices (views) of the emitted arrays.  No elementwise pass touches the outputs."""
     import diso_b200
     from diso_b200 import _lib
     alg_id = {"mc": _lib.ALG_MC, "dmc": _lib.ALG_DMC}[alg]
     gm = {"reference": _lib.GRAD_REFERENCE, "exact": _lib.GRAD_EXACT}[grad_mode]
-    dev, dt = sdf_own.device, sdf_own.dtype
+    dev, dt = sdf_ext.device, sdf_ext.dtype
     k = 3 if alg == "mc" else 4
-    diso_b200._check_inputs(sdf_own, deform_own, dt)
-    sdf_ext = _HaloExchange.apply(sdf_own, rank, world, group) if world > 1 else sdf_own
-    def_ext = None
-    if deform_own is not None:
-        def_ext = _HaloExchange.apply(deform_own, rank, world, group) if world > 1 else deform_own
+    diso_b200._check_inputs(sdf_ext, def_ext, dt)
     lo = a - (HALO if rank > 0 else 0)                      # global x of the first local layer
     A = a + 1 if rank > 0 else 0                            # owned padded layers [A, B), global padded coords
     B = b + 1 if rank < world - 1 else X + 2
@@ -162,18 +182,30 @@ def _extract_slab_fused(alg, sdf_own, deform_own, a, b, X, isovalue, normalize, 
     with torch.cuda.device(dev):
         g = sdf_ext.contiguous()
         d = def_ext.contiguous() if def_ext is not None else None
+        L = _lib.load()
         with torch.no_grad():
-            state, counts = diso_b200._count(alg_id, g, isovalue)
-        e0 = e1 = f0 = f1 = 0
-        if counts[_lib.CNT_EDGES] > 0:
-            e_pre, f_pre = diso_b200.layer_prefixes(alg_id, state, tuple(g.shape))
-            e0, e1 = int(e_pre[lA]), int(e_pre[lB])       # crossing edges: MC vertices / DMC quads
-            f0, f1 = int(f_pre[lA]), int(f_pre[lB])       # MC triangles / DMC dual vertices
+            Xl, Y, Z = g.shape
+            nbytes = diso_b200._state_bytes(alg_id, Xl, Y, Z)
+            state = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.check(L.diso_b200_count(alg_id, g.data_ptr(), diso_b200._DTYPES[dt], Xl, Y, Z, float(isovalue),
+                                         state.data_ptr(), nbytes, diso_b200._stream()))
+            head = state[: 8 * _lib.COUNT_SLOTS].view(torch.int64)
+            pre = state.view(torch.int32)[_prefix_index(alg_id, (Xl, Y, Z), lA, lB, dev)].to(torch.int64) & 0xffffffff
+            e_cnt, f_cnt = pre[1] - pre[0], pre[3] - pre[2]   # crossing edges (MC verts / DMC quads), MC tris / DMC dual verts
+            mine_dev = torch.stack(([e_cnt, f_cnt] if alg == "mc" else [f_cnt, e_cnt]) + [head[_lib.CNT_ANY_GT]])
+            if world > 1 and dist.get_backend(group) != "gloo":
+                gathered = torch.empty((world, 3), dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(gathered, mine_dev, group=group)
+                packed = torch.cat([head, pre, gathered.flatten()]).cpu()          # the one host sync
+                allc = packed[_lib.COUNT_SLOTS + 4:].view(world, 3)
+            else:
+                packed = torch.cat([head, pre]).cpu()
+                allc = _gather_counts(mine_dev, group, world)
+            counts = packed[: _lib.COUNT_SLOTS].tolist()
+            e0, e1, f0, f1 = packed[_lib.COUNT_SLOTS: _lib.COUNT_SLOTS + 4].tolist()
         v0, v1, q0, q1 = (e0, e1, f0, f1) if alg == "mc" else (f0, f1, e0, e1)   # owned vertex / face ranges (local ids)
         # "some value > iso" over the extended slab; the halo layers are other ranks' layers, so the OR over the
         # ranks is the global test of the reference's early-out (diso/__init__.py:49)
-        mine = torch.tensor([v1 - v0, q1 - q0, counts[_lib.CNT_ANY_GT]], dtype=torch.int64, device=dev)
-        allc = _gather_counts(mine, group, world)
         v_off = int(allc[:rank, 0].sum())
         info = dict(vert_offset=v_off, face_offset=int(allc[:rank, 1].sum()), n_verts_total=int(allc[:, 0].sum()),
                     n_faces_total=int(allc[:, 1].sum()), owned_layers=(A, B))
@@ -190,6 +222,100 @@ def _extract_slab_fused(alg, sdf_own, deform_own, a, b, X, isovalue, normalize, 
         verts_l, faces_l = diso_b200._Extract.apply(g, d, alg_id, float(isovalue), bool(normalize), gm, state, counts,
                                                     (lo, X, v_off - v0))
         return verts_l[v0:v1], faces_l[q0:q1], info
+
+
+def _extract_slab_fused(alg, sdf_own, deform_own, a, b, X, isovalue, normalize, group, rank, world, grad_mode="reference"):
+    """extract_slab's product path for callers holding only THEIR layers: the halo exchange builds the extended slab
+    (one copy of the slab; callers that keep the extended slab themselves avoid it, see SlabField)."""
+    sdf_ext = _HaloExchange.apply(sdf_own, rank, world, group) if world > 1 else sdf_own
+    def_ext = None
+    if deform_own is not None:
+        def_ext = _HaloExchange.apply(deform_own, rank, world, group) if world > 1 else deform_own
+    return _extract_ext(alg, sdf_ext, def_ext, a, b, X, isovalue, normalize, group, rank, world, grad_mode)
+
+
+class _HaloGrad(Function):
+    """Identity on an extended slab whose halo layers were refreshed in place; backward returns the halo layers'
+    gradients to their owners (two neighbour messages) and adds what the neighbours send for OUR boundary layers.
+    The incoming gradient is updated in place (it is the dense tensor our own backward just produced)."""
+
+    @staticmethod
+    def forward(ctx, ext, rank, world, group):
+        ctx.rank, ctx.world, ctx.group = rank, world, group
+        return ext.view_as(ext)
+
+    @staticmethod
+    def backward(ctx, g):
+        rank, world, group = ctx.rank, ctx.world, ctx.group
+        n_lo = HALO if rank > 0 else 0
+        n_hi = HALO if rank < world - 1 else 0
+        if not g.is_contiguous():
+            g = g.contiguous()
+        n = g.shape[0]
+        from_prev = g.new_empty((HALO,) + g.shape[1:]) if n_lo else None
+        from_next = g.new_empty((HALO,) + g.shape[1:]) if n_hi else None
+        spec = []
+        if n_lo:        # my lo halo belongs to prev's last layers; prev's hi halo are my first layers
+            spec += [("send", g[:HALO], rank - 1), ("recv", from_prev, rank - 1)]
+        if n_hi:
+            spec += [("send", g[n - HALO:], rank + 1), ("recv", from_next, rank + 1)]
+        _p2p(spec, group)
+        if n_lo:
+            g[n_lo: n_lo + HALO] += from_prev
+            g[:n_lo] = 0
+        if n_hi:
+            g[n - n_hi - HALO: n - n_hi] += from_next
+            g[n - n_hi:] = 0
+        return g, None, None, None
+
+
+class SlabField:
+    """A rank's slab of one large grid, stored EXTENDED by its halo layers so that no per-step copy of the slab is
+    needed: ``ext`` ([n_lo + n + n_hi, Y, Z(, 3)], the tensor to optimise -- make it the leaf) and ``own`` (the view
+    of the rank's own layers).  ``refresh()`` re-fills the halo layers from the neighbours in place; gradients that
+    land on the halo layers are sent back to their owners inside backward and zeroed locally.
+    REQUIREMENT: every rank must run backward through the vertices it got (even an empty set), otherwise the
+    neighbours block in the gradient exchange."""
+
+    def __init__(self, own_values, rank, world, group=None):
+        self.rank, self.world, self.group = rank, world, group
+        self.n_lo = HALO if rank > 0 else 0
+        self.n_hi = HALO if rank < world - 1 else 0
+        n = own_values.shape[0]
+        self.ext = own_values.new_empty((self.n_lo + n + self.n_hi,) + tuple(own_values.shape[1:]))
+        self.ext[self.n_lo: self.n_lo + n].copy_(own_values.detach())
+        self.n = n
+
+    @property
+    def own(self):
+        return self.ext[self.n_lo: self.n_lo + self.n]
+
+    def refresh(self):
+        if self.world == 1:
+            return
+        with torch.no_grad():
+            e, n_lo, n = self.ext.detach(), self.n_lo, self.n
+            spec = []
+            if self.n_lo:
+                spec += [("send", e[n_lo: n_lo + HALO], self.rank - 1), ("recv", e[:n_lo], self.rank - 1)]
+            if self.n_hi:
+                spec += [("send", e[n_lo + n - HALO: n_lo + n], self.rank + 1), ("recv", e[n_lo + n:], self.rank + 1)]
+            _p2p(spec, self.group)
+
+    def synced(self):
+        """The extended tensor with fresh halos, wired into autograd (use this in the forward)."""
+        self.refresh()
+        return _HaloGrad.apply(self.ext, self.rank, self.world, self.group) if self.world > 1 else self.ext
+
+
+def extract_slab_ext(alg, sdf_field, deform_field, x_range, X, isovalue=0.0, normalize=True, group=None, grad_mode="reference"):
+    """extract_slab for :class:`SlabField` inputs (the extended slab is the leaf: no per-step copy of the slab,
+    one host synchronisation per extraction).  Same return values as :func:`extract_slab`."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    a, b = x_range
+    sdf_ext = sdf_field.synced()
+    def_ext = deform_field.synced() if deform_field is not None else None
+    return _extract_ext(alg, sdf_ext, def_ext, a, b, X, isovalue, normalize, group, rank, world, grad_mode)
 
 
 def extract_slab(alg, sdf_own, deform_own, x_range, X, isovalue=0.0, normalize=True, group=None, extractor=None):

@@ -66,8 +66,9 @@ def oracle_extractor(alg):
     return run
 
 
-def worker(rank, world, port, alg, sdf, deform, iso, normalize, use_cuda, out_dir):
-    """Body of one rank: shard, extract, backward with a fixed dL/dverts, dump results."""
+def worker(rank, world, port, alg, sdf, deform, iso, normalize, use_cuda, out_dir, field=False):
+    """Body of one rank: shard, extract, backward with a fixed dL/dverts, dump results.
+    field=True: the rank keeps its slab as a parallel.SlabField (extended leaf, in-place halo refresh)."""
     import torch.distributed as dist
     from diso_b200 import parallel
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
@@ -78,13 +79,30 @@ def worker(rank, world, port, alg, sdf, deform, iso, normalize, use_cuda, out_di
         s_own = sdf[a:b].clone().to(dev).requires_grad_(True)
         d_own = deform[a:b].clone().to(dev).requires_grad_(True) if deform is not None else None
         ext = None if use_cuda else oracle_extractor(alg)
-        verts, faces, info = parallel.extract_slab(alg, s_own, d_own, (a, b), X, iso, normalize, extractor=ext)
+        if field:
+            sf = parallel.SlabField(s_own.detach(), rank, world)
+            sf.ext.requires_grad_(True)
+            df = None
+            if d_own is not None:
+                df = parallel.SlabField(d_own.detach(), rank, world)
+                df.ext.requires_grad_(True)
+            verts, faces, info = parallel.extract_slab_ext(alg, sf, df, (a, b), X, iso, normalize)
+        else:
+            verts, faces, info = parallel.extract_slab(alg, s_own, d_own, (a, b), X, iso, normalize, extractor=ext)
         if verts.shape[0] or verts.requires_grad:   # (an empty but attached result keeps the halo backward symmetric)
             i = torch.arange(info["vert_offset"] * 3, (info["vert_offset"] + verts.shape[0]) * 3, dtype=torch.float64).reshape(-1, 3)
             w = torch.cos(i * 0.6180339887 + 0.25).to(verts.dtype).to(dev)
             (verts * w).sum().backward()
-        else:
+        elif not field:
             (s_own.sum() * 0).backward()
+        if field:   # gradients of the rank's own layers (halo layers of the extended leaf carry zeros after the exchange)
+            z = torch.zeros_like(sf.ext)
+            ge = sf.ext.grad if sf.ext.grad is not None else z
+            assert float(ge[: sf.n_lo].abs().sum()) == 0 and float(ge[sf.n_lo + sf.n:].abs().sum()) == 0
+            s_own.grad = ge[sf.n_lo: sf.n_lo + sf.n].clone()
+            if df is not None:
+                gd = df.ext.grad if df.ext.grad is not None else torch.zeros_like(df.ext)
+                d_own.grad = gd[df.n_lo: df.n_lo + df.n].clone()
         torch.save(dict(verts=verts.detach().cpu(), faces=faces.cpu(), info=info,
                         gsdf=s_own.grad.cpu() if s_own.grad is not None else torch.zeros_like(s_own).cpu(),
                         gdef=(d_own.grad.cpu() if d_own.grad is not None else torch.zeros_like(d_own).cpu()) if d_own is not None else None),

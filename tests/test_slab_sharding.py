@@ -28,8 +28,8 @@ def _weights(n, dtype):
     return torch.cos(i * 0.6180339887 + 0.25).to(dtype)
 
 
-def _run_sharded(world, alg, sdf, deform, iso, normalize, use_cuda, tmp_path):
-    mp.spawn(worker, args=(world, _port(), alg, sdf, deform, iso, normalize, use_cuda, str(tmp_path)), nprocs=world, join=True)
+def _run_sharded(world, alg, sdf, deform, iso, normalize, use_cuda, tmp_path, field=False):
+    mp.spawn(worker, args=(world, _port(), alg, sdf, deform, iso, normalize, use_cuda, str(tmp_path), field), nprocs=world, join=True)
     parts = [torch.load(tmp_path / ("rank%d.pt" % r), weights_only=False) for r in range(world)]
     verts = torch.cat([p["verts"] for p in parts])
     faces = torch.cat([p["faces"] for p in parts])
