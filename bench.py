@@ -181,6 +181,8 @@ def kernel_bytes(name, G, s, c_mc, c_dmc, deform):
         "dmc_emit_verts": 3 * Vd * s,
         "dmc_emit_quads": 4 * Qd * 8,
         "dmc_edge_adjoint": 3 * Vd * s,
+        # fused DMC backward (per-edge adjoint evaluated inside the edge pass): dL/d dual vertices in, dense adjoints out
+        "dmc_backward": 3 * Vd * s + min(Em, G) * s + G * s + d3 * (min(Em, G) + G) * s,
     }
     return table.get(name, 0)
 

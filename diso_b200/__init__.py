@@ -9,6 +9,7 @@ in hand-written sm_100a CUDA kernels behind the C ABI of ``include/diso_b200.h``
 """
 import contextlib
 import ctypes
+import os
 
 import torch
 from torch import nn
@@ -181,11 +182,13 @@ class _Extract(Function):
                                                    _lib.frame_ptr(ctx.frame), _ptr(rec), max(ctx.n_edges, 1),
                                                    _ptr(adj_grid), _ptr(adj_deform), _stream()))
             else:
-                scratch = torch.empty((_blocks32(ctx.n_edges), 3, 32), dtype=grid.dtype, device=grid.device)  # per-edge adjoints
+                # per-edge adjoints: only the unfused path (no saved records) materialises them
+                fused = rec is not None and not os.environ.get("DISO_DMC_BWD_UNFUSED")
+                scratch = None if fused else torch.empty((_blocks32(ctx.n_edges), 3, 32), dtype=grid.dtype, device=grid.device)
                 _lib.check(L.diso_b200_dmc_backward(grid.data_ptr(), _ptr(deform), dt, X, Y, Z, ctx.isovalue,
                                                     state.data_ptr(), ctypes.cast(ctx.counts, ctypes.c_void_p),
                                                     adj_verts.data_ptr(), int(ctx.normalize), _lib.frame_ptr(ctx.frame),
-                                                    ctx.grad_mode, _ptr(rec), max(ctx.n_edges, 1), scratch.data_ptr(),
+                                                    ctx.grad_mode, _ptr(rec), max(ctx.n_edges, 1), _ptr(scratch),
                                                     _ptr(adj_grid), _ptr(adj_deform), _stream()))
         return (adj_grid if need_grid else None, adj_deform if need_deform else None) + none7
 

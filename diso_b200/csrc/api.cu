@@ -320,39 +320,47 @@ int launch_bwd_compact(const T *sdf, const T *deform, const Geo &g, T isoT, T pa
 }
 
 // v2 backward from saved edge records (mc_backward_v2.cuh).
-template <typename T, bool HAS_DEF, bool G_SOA, int BX, int BY>
-int launch_bwd2(const Geo &g, T isoT, T ix, T iy, T iz, const uint4 *E, const T *gsrc, const T *rec,
+template <typename T, bool HAS_DEF, int GSRC, int BX, int BY>
+int launch_bwd2(const Geo &g, T isoT, T ix, T iy, T iz, const uint4 *E, const T *gsrc, const DmcSrc &dmc, const T *rec,
                 T *adj_sdf, T *adj_deform, unsigned *work, bool sparse, cudaStream_t st)
 {
-    using L = Bwd2Layout<T, HAS_DEF, BX, BY>;
+    const char *name = GSRC >= 2 ? "dmc_backward" : "mc_backward";
+    // Shared-memory carve-out: the edge pass keeps 8 (MC) / 20 (DMC, fused dual-vertex adjoint) loads per thread in flight and
+    // every pending line occupies L1, so L1 capacity bounds the memory-level parallelism: with the driver's default (all 228 KB
+    // shared for 8 CTAs/SM, 28 KB L1) the fp32 kernels take 1.92 / 3.53 ms at 512^3, with ~164 KB shared (6 CTAs, 92 KB L1) 1.54 /
+    // 2.63, with 132 KB 1.60 / 2.54 (sweep in profiles/r2_backward.md)
+    const char *carve_env = GSRC >= 2 ? "DISO_CARVEOUT_DBWD" : "DISO_CARVEOUT_BWD2";
+    const int carve = GSRC >= 2 ? 58 : 72;
+    using L = Bwd2Layout<T, HAS_DEF, (GSRC >= 2), BX, BY>;
     const size_t smem = L::bytes;
     const int ntx = cdiv(g.X, BX), nty = cdiv(g.Y, BY);
     const long long nblk = (long long)ntx * nty * g.NC;
     if (sparse) {
-        auto kern = mc_backward2_queue_kernel<T, HAS_DEF, G_SOA, BX, BY>;
-        kernel_attrs(reinterpret_cast<const void *>(kern), "DISO_CARVEOUT_BWD2", -1, smem);
+        auto kern = mc_backward2_queue_kernel<T, HAS_DEF, GSRC, BX, BY>;
+        kernel_attrs(reinterpret_cast<const void *>(kern), carve_env, carve, smem);
         const size_t G = (size_t)g.X * g.Y * g.Z;
         if (adj_sdf) CU_TRY(cudaMemsetAsync(adj_sdf, 0, G * sizeof(T), st));
         if (HAS_DEF && adj_deform) CU_TRY(cudaMemsetAsync(adj_deform, 0, G * 3 * sizeof(T), st));
         CU_TRY(cudaMemsetAsync(work, 0, 64, st));
         LAUNCH("mc_backward_mark", st, (bwd_mark_kernel<BX, BY><<<cdiv(nblk, 256), 256, 0, st>>>(g, E, ntx, nty, work)));
         const int ctas = (int)std::min<long long>(nblk, (long long)sm_count() * 6);
-        LAUNCH("mc_backward", st, kern<<<ctas, B2_THREADS, smem, st>>>(g, isoT, ix, iy, iz, E, gsrc, rec, adj_sdf, adj_deform, nty, work));
+        LAUNCH(name, st, kern<<<ctas, B2_THREADS, smem, st>>>(g, isoT, ix, iy, iz, E, gsrc, dmc, rec, adj_sdf, adj_deform, nty, work));
         return DISO_OK;
     }
-    auto kern = mc_backward2_kernel<T, HAS_DEF, G_SOA, BX, BY>;
-    kernel_attrs(reinterpret_cast<const void *>(kern), "DISO_CARVEOUT_BWD2", -1, smem);
+    auto kern = mc_backward2_kernel<T, HAS_DEF, GSRC, BX, BY>;
+    kernel_attrs(reinterpret_cast<const void *>(kern), carve_env, carve, smem);
     const bool flat = nty > 65535 || ntx > 65535;
     const dim3 grid = flat ? dim3((unsigned)nblk, 1, 1) : dim3((unsigned)g.NC, (unsigned)nty, (unsigned)ntx);
-    LAUNCH("mc_backward", st, kern<<<grid, B2_THREADS, smem, st>>>(g, isoT, ix, iy, iz, E, gsrc, rec, adj_sdf, adj_deform,
-                                                                   ntx, nty, flat ? 1 : 0));
+    LAUNCH(name, st, kern<<<grid, B2_THREADS, smem, st>>>(g, isoT, ix, iy, iz, E, gsrc, dmc, rec, adj_sdf, adj_deform,
+                                                          ntx, nty, flat ? 1 : 0));
     return DISO_OK;
 }
 
-// gsrc: per-edge adjoints, [n,3] or (g_soa) blocked SoA.  rec != NULL selects the v2 kernel.
+// gsrc_kind (mc_backward_v2.cuh GSRC): 0 per-edge adjoints [n,3], 1 blocked SoA, 2 / 3 DMC fused (gsrc = dL/d dual vertices,
+// exact / reference-compatible).  rec != NULL selects the v2 kernel.
 template <typename T>
 int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const int64_t *counts_host,
-                     const T *gsrc, bool g_soa, const T *rec, int normalize, int X_global, T *adj_sdf, T *adj_deform,
+                     const T *gsrc, int gsrc_kind, const T *rec, int normalize, int X_global, T *adj_sdf, T *adj_deform,
                      cudaStream_t st)
 {
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
@@ -366,15 +374,16 @@ int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, co
     bool sparse = counts_host && counts_host[DISO_CNT_EDGE_CHUNKS] * 8 < (long long)g.NCH && g.NCH >= 65536;
     if (force >= 0) sparse = force != 0;
     if (rec) {
+        DmcSrc dmc{p.S, reinterpret_cast<const uint4 *>(p.aux), p.C};
+#define DISO_B2(HD, K) launch_bwd2<T, HD, K, BWD2_BX, BWD2_BY>(g, isoT, ix, iy, iz, p.E, gsrc, dmc, rec, adj_sdf, HD ? adj_deform : nullptr, p.bwd, sparse, st)
         if (deform) {
-            if (g_soa) return launch_bwd2<T, true, true, BWD2_BX, BWD2_BY>(g, isoT, ix, iy, iz, p.E, gsrc, rec, adj_sdf, adj_deform, p.bwd, sparse, st);
-            return launch_bwd2<T, true, false, BWD2_BX, BWD2_BY>(g, isoT, ix, iy, iz, p.E, gsrc, rec, adj_sdf, adj_deform, p.bwd, sparse, st);
+            switch (gsrc_kind) { case 1: return DISO_B2(true, 1); case 2: return DISO_B2(true, 2); case 3: return DISO_B2(true, 3); default: return DISO_B2(true, 0); }
         }
-        if (g_soa) return launch_bwd2<T, false, true, BWD2_BX, BWD2_BY>(g, isoT, ix, iy, iz, p.E, gsrc, rec, adj_sdf, nullptr, p.bwd, sparse, st);
-        return launch_bwd2<T, false, false, BWD2_BX, BWD2_BY>(g, isoT, ix, iy, iz, p.E, gsrc, rec, adj_sdf, nullptr, p.bwd, sparse, st);
+        switch (gsrc_kind) { case 1: return DISO_B2(false, 1); case 2: return DISO_B2(false, 2); case 3: return DISO_B2(false, 3); default: return DISO_B2(false, 0); }
+#undef DISO_B2
     }
     // no saved records (callers of the bare ABI, the diso._C shim): v1, which re-gathers sdf / deform
-    if (g_soa) return fail(DISO_E_INVALID, "internal: SoA adjoints need the saved edge records");
+    if (gsrc_kind) return fail(DISO_E_INVALID, "internal: this adjoint source needs the saved edge records");
     if (!adj_sdf || (deform && !adj_deform)) return fail(DISO_E_INVALID, "adj_sdf / adj_deform may only be NULL when edge_rec is given");
     // block shape (common.cuh: BWD_BX x BWD_BY) from sweeps on B200 (512^3 rand-flexi): 4x6 1.70 ms, 3x8 1.71, 4x7 / 4x8 1.73,
     // 8x4 1.76, 6x8 1.82, 2x8 1.90, 4x4 1.92
@@ -390,6 +399,15 @@ int dmc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, c
     const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
     const T ix = normalize ? T(1) / (T(X_global) - T(1)) : T(1), iy = normalize ? T(1) / (T(g.Y) - T(1)) : T(1),
             iz = normalize ? T(1) / (T(g.Z) - T(1)) : T(1);
+    if (rec) {
+        // saved records: ONE kernel, like the reference's adj_create_dmc_verts (cudualmc.cu:957-1005): the per-edge adjoint
+        // is evaluated inside the edge pass of mc_backward2 (no per-edge array, one edge list instead of two)
+        static const int unfused = env_int("DISO_DMC_BWD_UNFUSED", 0);   // experiment knob: stage A as its own kernel
+        if (!unfused)
+            return mc_backward_impl<T>(sdf, deform, g, iso, p, counts_host, adj_verts, grad_mode == DISO_GRAD_EXACT ? 2 : 3, rec, normalize,
+                                       X_global, adj_sdf, adj_deform, st);
+        if (!scratch) return fail(DISO_E_INVALID, "scratch required");
+    }
     const TileGrid te = tile_grid(p, g, counts_host, 0);
     // stage A writes the per-edge adjoints in blocked SoA form when stage B is the v2 kernel (coalesced on both sides)
     const int g_soa = rec ? 1 : 0;
@@ -399,7 +417,7 @@ int dmc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, c
         else                              { if (te.list) DISO_ADJ(2, true) else DISO_ADJ(2, false) }
 #undef DISO_ADJ
     }
-    return mc_backward_impl<T>(sdf, deform, g, iso, p, counts_host, scratch, g_soa != 0, rec, 0, g.X, adj_sdf, adj_deform, st);
+    return mc_backward_impl<T>(sdf, deform, g, iso, p, counts_host, scratch, g_soa, rec, 0, g.X, adj_sdf, adj_deform, st);
 }
 
 }  // namespace
@@ -544,10 +562,10 @@ int diso_b200_mc_backward(const void *sdf, const void *deform, int dtype, int X,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == DISO_F32)
         return mc_backward_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, counts_host,
-                                       static_cast<const float *>(adj_verts), false, static_cast<const float *>(edge_rec),
+                                       static_cast<const float *>(adj_verts), 0, static_cast<const float *>(edge_rec),
                                        normalize, fr.X_global, static_cast<float *>(adj_sdf), static_cast<float *>(adj_deform), st);
     return mc_backward_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, counts_host,
-                                    static_cast<const double *>(adj_verts), false, static_cast<const double *>(edge_rec),
+                                    static_cast<const double *>(adj_verts), 0, static_cast<const double *>(edge_rec),
                                     normalize, fr.X_global, static_cast<double *>(adj_sdf), static_cast<double *>(adj_deform), st);
 }
 
@@ -558,7 +576,7 @@ int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X
 {
     int rc = check_dims(DISO_ALG_DMC, dtype, X, Y, Z);
     if (rc) return rc;
-    if (!sdf || !state || !adj_verts || !scratch) return fail(DISO_E_INVALID, "null pointer");
+    if (!sdf || !state || !adj_verts || (!scratch && !edge_rec)) return fail(DISO_E_INVALID, "null pointer");
     if (!deform && adj_deform) return fail(DISO_E_INVALID, "adj_deform given without deform");
     if (!edge_rec && (!adj_sdf || (deform != nullptr) != (adj_deform != nullptr)))
         return fail(DISO_E_INVALID, "without edge_rec, adj_sdf is required and adj_deform must be given iff deform is");

@@ -26,6 +26,7 @@
 // but ~300 instructions per chunk (150 of them the per-point gather): issue-bound at 1.80 ms, slower than v1.)
 #pragma once
 #include "mc_backward_compact.cuh"   // rcp_fast, bwd_mark_kernel, BC_THREADS
+#include "tables.cuh"
 
 namespace diso {
 
@@ -57,7 +58,7 @@ template <typename T> __device__ __forceinline__ T ent_d(const Quad<T> &a) { ret
 __device__ __forceinline__ float ent_d(const float &a) { return a; }
 __device__ __forceinline__ double ent_d(const double &a) { return a; }
 
-template <typename T, bool HAS_DEF, int BX, int BY> struct Bwd2Layout {
+template <typename T, bool HAS_DEF, bool DMC, int BX, int BY> struct Bwd2Layout {
     static constexpr int ROWS = (BX + 1) * (BY + 1);          // candidate rows incl. the -x / -y halo
     static constexpr int PTS = BX * BY * 32;                  // output points per block
     using Ent = typename EntOf<T, HAS_DEF>::type;
@@ -70,21 +71,36 @@ template <typename T, bool HAS_DEF, int BX, int BY> struct Bwd2Layout {
     static constexpr size_t off_delta = off_zin + ROWS * 4;                // u32 [ROWS]       own rows: rank - list slot
     static constexpr size_t off_info = (off_delta + ROWS * 4 + 15) / 16 * 16;  // int4 [ROWS]  accumulator bases {own, +x target, +y target, -}
     static constexpr size_t off_rowb = off_info + ROWS * 16;               // i64 [ROWS]       output element of lane 0 (own rows)
-    static constexpr size_t off_stage = (off_rowb + ROWS * 8 + 15) / 16 * 16;  // T [WARPS][96] (deform write-out)
-    static constexpr size_t off_list = off_stage + (HAS_DEF ? B2_WARPS * 96 * sizeof(T) : 0);   // u16 [CAP]
+    static constexpr size_t off_rowk = off_rowb + ROWS * 8;                // i32 [ROWS]       chunk id of the row (DMC: cells around an edge)
+    static constexpr size_t off_sign = off_rowk + (DMC ? ROWS * 4 : 0);    // u32 [ROWS]       sign word of the row's chunk (DMC)
+    static constexpr size_t off_tab = (off_sign + (DMC ? ROWS * 4 : 0) + 15) / 16 * 16;    // DMC tables: case[256], plen[256], quad[8], inv[8]
+    static constexpr size_t off_stage = off_tab + (DMC ? 2 * 256 * 4 + 8 * 4 + 8 * sizeof(T) + 16 : 0);  // T [WARPS][96] (deform write-out)
+    static constexpr size_t off_list = (off_stage + (HAS_DEF ? B2_WARPS * 96 * sizeof(T) : 0) + 15) / 16 * 16;   // u16 [CAP]
     static constexpr size_t bytes = off_list + (size_t)CAP * 2 + 16;
     static_assert(ROWS <= 64 && 4 * ROWS <= B2_THREADS, "four threads per row build the list; row index fits the descriptor");
 };
 
-// G_SOA: the per-edge adjoints come in blocked SoA form (stage A of the DMC backward writes them that way);
-// otherwise [n, 3] AoS (autograd's dL/dverts of DiffMC).
-template <typename T, bool HAS_DEF, bool G_SOA, int BX, int BY, bool OUTPUTS_ZEROED>
+// Where dL/d(edge crossing) comes from.
+//   GSRC == 0: gsrc is [n, 3] AoS (autograd's dL/dverts of DiffMC);
+//   GSRC == 1: gsrc is blocked SoA (stage A of an unfused DMC backward);
+//   GSRC == 2 / 3: DMC, evaluated HERE (exact / reference-compatible adjoint of the dual-vertex averaging,
+//                  adj_create_dmc_verts, cudualmc.cu:957-1005, which is one kernel in the reference too): the edge's
+//                  adjoint is the sum over the 4 cells around it of adj_dual[patch of the edge in that cell] / len(patch).
+//                  No per-edge array is written or read, and the edge list is built once instead of twice.
+struct DmcSrc {
+    const unsigned *S;          // sign words
+    const uint4 *P;             // {first dual vertex of the chunk, used, lo, hi}
+    const unsigned short *C;    // per cell: case index | offset of the first dual vertex << 8
+};
+
+template <typename T, bool HAS_DEF, int GSRC, int BX, int BY, bool OUTPUTS_ZEROED>
 __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T iy, T iz, const uint4 *__restrict__ E,
-                                                   const T *__restrict__ gsrc, const T *__restrict__ rec,
+                                                   const T *__restrict__ gsrc, const DmcSrc dmc, const T *__restrict__ rec,
                                                    T *__restrict__ adj_sdf, T *__restrict__ adj_deform,
                                                    int tx, int ty, int c)
 {
-    using L = Bwd2Layout<T, HAS_DEF, BX, BY>;
+    constexpr bool DMC = GSRC >= 2;
+    using L = Bwd2Layout<T, HAS_DEF, (GSRC >= 2), BX, BY>;
     using Ent = typename L::Ent;
     constexpr int ROWS = L::ROWS, PTS = L::PTS;
     extern __shared__ __align__(32) unsigned char smem2_raw[];
@@ -95,6 +111,12 @@ __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T 
     unsigned *s_delta = reinterpret_cast<unsigned *>(smem2_raw + L::off_delta);
     int4 *s_info = reinterpret_cast<int4 *>(smem2_raw + L::off_info);
     long long *s_rowb = reinterpret_cast<long long *>(smem2_raw + L::off_rowb);
+    int *s_rowk = reinterpret_cast<int *>(smem2_raw + L::off_rowk);
+    unsigned *s_sign = reinterpret_cast<unsigned *>(smem2_raw + L::off_sign);
+    unsigned *s_case = reinterpret_cast<unsigned *>(smem2_raw + L::off_tab);
+    unsigned *s_plen = s_case + 256;
+    unsigned *s_quad = s_plen + 256;
+    T *s_inv = reinterpret_cast<T *>(s_quad + 8);
     T *s_stage = reinterpret_cast<T *>(smem2_raw + L::off_stage);
     unsigned short *s_list = reinterpret_cast<unsigned short *>(smem2_raw + L::off_list);
 
@@ -113,14 +135,17 @@ __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T 
             const int k = (xp * g.PY + yp) * g.NC + c;
             r4 = E[k];
             if (c > 0 && dxr >= 1 && dyr >= 1) zin = E[k - 1].w >> 31;
+            if (DMC) { s_rowk[tid] = k; s_sign[tid] = dmc.S[k]; }
         }
+        unsigned zsign = 0;   // DMC: is the start point of that arriving edge inside? (bit 31 of the previous chunk's sign word)
+        if (DMC && zin) zsign = dmc.S[(xp * g.PY + yp) * g.NC + c - 1] >> 31;
         unsigned cnt;
         if (dxr >= 1 && dyr >= 1) cnt = __popc(r4.y) + __popc(r4.z) + __popc(r4.w) + zin;   // own row: every edge
         else if (dxr == 0 && dyr == 0) cnt = 0;              // corner: touches nothing
         else if (dxr == 0) cnt = __popc(r4.y);               // -x halo row: its +x edges end in the block
         else cnt = __popc(r4.z);                             // -y halo row: its +y edges
         s_rec[tid] = r4;
-        s_zin[tid] = zin;
+        s_zin[tid] = zin | (zsign << 1);
         s_off[tid] = cnt;
         mine_any = cnt != 0u;
         // accumulator slots of lane 0 of: this row (own rows), the row its +x edges end in, the row its +y edges end in
@@ -150,6 +175,12 @@ __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T 
         }
         return;
     }
+    if (DMC) {   // case tables of the dual-vertex adjoint (read-only until the barrier below)
+        s_case[tid] = T_DMC_CASE[tid];
+        s_plen[tid] = T_DMC_PATCHLEN[tid];
+        if (tid < 6) s_quad[tid] = T_DMC_QUAD[tid];
+        if (tid < 8) s_inv[tid] = tid ? T(1) / T(tid) : T(0);
+    }
     if (wid == 0) {  // exclusive scan of the ROWS counts (<= two per lane)
         constexpr int PER = (ROWS + 31) / 32;
         unsigned v[PER], sum = 0;
@@ -162,7 +193,7 @@ __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T 
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             const int idx = lane * PER + i;
-            if (idx < ROWS) { s_off[idx] = run; s_delta[idx] = s_rec[idx].x - s_zin[idx] - run; }
+            if (idx < ROWS) { s_off[idx] = run; s_delta[idx] = s_rec[idx].x - (s_zin[idx] & 1u) - run; }
             run += v[i];
         }
         if (lane == 31) s_off[ROWS] = inc;
@@ -184,7 +215,7 @@ __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T 
         const unsigned dbase = ((unsigned)r << 6) | (unsigned)(sh + 1);
         const unsigned o = s_off[r];
         if (dxr >= 1 && dyr >= 1) {
-            const unsigned zin = s_zin[r];
+            const unsigned zin = s_zin[r] & 1u;
             if (zin && sh == 0) s_list[o] = (unsigned short)(((unsigned)r << 6) | (2u << 13));   // lane -1: +z edge of the previous chunk's last point
             const unsigned bx = (r4.y >> sh) & 0xffu, by = (r4.z >> sh) & 0xffu, bz = (r4.w >> sh) & 0xffu;
             unsigned slot = o + zin + __popc(r4.y & lt) + __popc(r4.z & lt) + __popc(r4.w & lt);
@@ -225,9 +256,37 @@ __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T 
                 if (axis == 1) rank += bit(r4.y, j);
             }
             T gx, gy, gz;
-            if (G_SOA) { const T *gp = gsrc + blk_index<3>(rank); gx = __ldg(gp); gy = __ldg(gp + 32); gz = __ldg(gp + 64); }
-            else { const T *gp = gsrc + (size_t)rank * 3; gx = __ldg(gp); gy = __ldg(gp + 1); gz = __ldg(gp + 2); }
-            gx = gx * ix; gy = gy * iy; gz = gz * iz;
+            if constexpr (DMC) {
+                // stage A of adj_create_dmc_verts (cudualmc.cu:957-1005), same operations and order as dmc_edges2_kernel<1|2>
+                int kq = s_rowk[r], jq = j;
+                unsigned inside;
+                if (j >= 0) inside = (s_sign[r] >> j) & 1u;
+                else { kq -= 1; jq = 31; inside = (s_zin[r] >> 1) & 1u; }
+                const unsigned q4 = s_quad[inside * 3 + axis];
+                Vec3<T> acc{T(0), T(0), T(0)};
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const unsigned b = (q4 >> (8 * cc)) & 0xffu;
+                    int kk = kq - (int)(b & 1u) * g.sX - (int)((b >> 1) & 1u) * g.sY;
+                    int jj = jq - (int)((b >> 2) & 1u);
+                    if (jj < 0) { kk -= 1; jj = 31; }
+                    const unsigned info = dmc.C[(size_t)kk * 32 + jj];
+                    const unsigned first = dmc.P[kk].x + (info >> 8);
+                    const unsigned code = info & 0xffu;
+                    const unsigned ord = (s_case[code] >> (2 * (b >> 4))) & 3u;
+                    const unsigned src = (GSRC == 2) ? first + ord : first;   // reference mode: the cell's FIRST dual vertex (cudualmc.cu:975,990)
+                    const T inv = s_inv[(s_plen[code] >> (4 * ord)) & 7u];
+                    const T *pa = gsrc + (size_t)src * 3;
+                    acc.x = fma_rn(__ldg(pa), inv, acc.x);
+                    acc.y = fma_rn(__ldg(pa + 1), inv, acc.y);
+                    acc.z = fma_rn(__ldg(pa + 2), inv, acc.z);
+                }
+                gx = acc.x * ix; gy = acc.y * iy; gz = acc.z * iz;
+            } else {
+                if (GSRC == 1) { const T *gp = gsrc + blk_index<3>(rank); gx = __ldg(gp); gy = __ldg(gp + 32); gz = __ldg(gp + 64); }
+                else { const T *gp = gsrc + (size_t)rank * 3; gx = __ldg(gp); gy = __ldg(gp + 1); gz = __ldg(gp + 2); }
+                gx = gx * ix; gy = gy * iy; gz = gz * iz;
+            }
             const T *rp = rec + blk_index<5>(rank);
             const T dpx = __ldg(rp), dpy = __ldg(rp + 32), dpz = __ldg(rp + 64), d0 = __ldg(rp + 96), d1 = __ldg(rp + 128);
             // adjComputeMcVert (cumc.cu:412-453) with one reciprocal: (iso - d1) / (d1 - d0)^2 * adj_t etc.
@@ -299,9 +358,9 @@ __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T 
 }
 
 // Dense launch: one CTA per block of the (chunk, y tile, x tile) grid.
-template <typename T, bool HAS_DEF, bool G_SOA, int BX, int BY>
+template <typename T, bool HAS_DEF, int GSRC, int BX, int BY>
 __global__ void __launch_bounds__(B2_THREADS) mc_backward2_kernel(Geo g, T iso, T ix, T iy, T iz, const uint4 *__restrict__ E,
-                                                                const T *__restrict__ gsrc, const T *__restrict__ rec,
+                                                                const T *__restrict__ gsrc, DmcSrc dmc, const T *__restrict__ rec,
                                                                 T *__restrict__ adj_sdf, T *__restrict__ adj_deform, int ntx,
                                                                 int nty, int flat)
 {
@@ -313,14 +372,14 @@ __global__ void __launch_bounds__(B2_THREADS) mc_backward2_kernel(Geo g, T iso, 
     } else {
         c = blockIdx.x; ty = blockIdx.y; tx = blockIdx.z;
     }
-    mc_backward2_block<T, HAS_DEF, G_SOA, BX, BY, false>(g, iso, ix, iy, iz, E, gsrc, rec, adj_sdf, adj_deform, tx, ty, c);
+    mc_backward2_block<T, HAS_DEF, GSRC, BX, BY, false>(g, iso, ix, iy, iz, E, gsrc, dmc, rec, adj_sdf, adj_deform, tx, ty, c);
 }
 
 // Sparse surfaces: outputs zero-filled by cudaMemsetAsync, bwd_mark_kernel (mc_backward_compact.cuh) lists the
 // touched blocks, a persistent grid pulls them from that list.
-template <typename T, bool HAS_DEF, bool G_SOA, int BX, int BY>
+template <typename T, bool HAS_DEF, int GSRC, int BX, int BY>
 __global__ void __launch_bounds__(B2_THREADS) mc_backward2_queue_kernel(Geo g, T iso, T ix, T iy, T iz, const uint4 *__restrict__ E,
-                                                                      const T *__restrict__ gsrc, const T *__restrict__ rec,
+                                                                      const T *__restrict__ gsrc, DmcSrc dmc, const T *__restrict__ rec,
                                                                       T *__restrict__ adj_sdf, T *__restrict__ adj_deform, int nty,
                                                                       unsigned *__restrict__ work)
 {
@@ -334,7 +393,7 @@ __global__ void __launch_bounds__(B2_THREADS) mc_backward2_queue_kernel(Geo g, T
         unsigned b = work[16 + i];
         const int c = (int)(b % (unsigned)g.NC); b /= (unsigned)g.NC;
         const int ty = (int)(b % (unsigned)nty), tx = (int)(b / (unsigned)nty);
-        mc_backward2_block<T, HAS_DEF, G_SOA, BX, BY, true>(g, iso, ix, iy, iz, E, gsrc, rec, adj_sdf, adj_deform, tx, ty, c);
+        mc_backward2_block<T, HAS_DEF, GSRC, BX, BY, true>(g, iso, ix, iy, iz, E, gsrc, dmc, rec, adj_sdf, adj_deform, tx, ty, c);
         __syncthreads();   // shared memory (and s_next) is reused by the next block
     }
 }

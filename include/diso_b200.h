@@ -147,8 +147,8 @@ int diso_b200_mc_backward(const void *sdf, const void *deform, int dtype, int X,
                           int64_t edge_rec_stride, void *adj_sdf, void *adj_deform, void *stream);
 
 /* Backward, dual marching cubes (replaces adj_create_dmc_verts, cudualmc.cu:957-1005).
- * scratch: caller-owned per-edge adjoints: n_quads*3 elements of dtype, or 3 * 32 * ceil(n_quads / 32) when
- * edge_rec is given (groups of 32 edges, like the records).
+ * scratch: caller-owned per-edge adjoints, n_quads*3 elements of dtype; may be NULL when edge_rec is given (the
+ * per-edge adjoint is then evaluated inside the one backward kernel and never materialised).
  * edge_rec / edge_rec_stride: as for diso_b200_mc_backward. */
 int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
                            double iso, void *state, const int64_t *counts_host,
