@@ -16,7 +16,15 @@ caller's padded tensor adds one more (inert) shell -- no crossing edge can touch
 caller's own shell is already >= iso -- so the mesh is the reference's; coordinates are formed one
 lattice unit further from the origin and shifted back, hence equal to the reference's to 1 ulp
 rather than bit-for-bit.  Input checks mirror pybind.cpp:5-11,57-60 (CUDA, contiguous, dtype).
+
+Limit: that equivalence needs the caller's boundary layer to be >= iso (what diso/__init__.py:52 guarantees for
+every call that goes through DiffMC / DiffDMC).  A raw grid whose boundary dips below iso makes the reference read
+out of bounds / leave the surface open, while the virtual shell here would close it with extra faces -- different
+meshes.  ``forward`` therefore checks the six boundary faces and raises instead of returning a different mesh
+(``DISO_B200_C_NO_BOUNDARY_CHECK=1`` skips the check and its small host synchronisation).
 """
+import os
+
 import ctypes
 
 import torch
@@ -47,6 +55,11 @@ class _Base:
         if deform is not None:
             self._check("deform", deform)
         k = 3 if self._alg == _lib.ALG_MC else 4
+        if not os.environ.get("DISO_B200_C_NO_BOUNDARY_CHECK") and grid.numel():
+            lo = min(float(f.min()) for f in (grid[0], grid[-1], grid[:, 0], grid[:, -1], grid[:, :, 0], grid[:, :, -1]))
+            if lo < float(iso):
+                raise DisoB200Error("diso_b200._C expects the reference's padded input (boundary layer >= iso, diso/__init__.py:52); "
+                                    "this grid's boundary goes down to %g < iso = %g: pad it, or call DiffMC / DiffDMC" % (lo, float(iso)))
         with torch.cuda.device(grid.device), torch.no_grad():
             state, counts = _count(self._alg, grid, iso)
             nv, nf = counts[_lib.CNT_VERTS], counts[_lib.CNT_FACES]

@@ -65,7 +65,6 @@ struct StatePtrs {
     void *aux;
     unsigned short *C;
     unsigned *active;     // [0, NCH): chunks owning crossing edges, [NCH, 2 NCH): chunks with faces (ascending)
-    unsigned *bwd;        // work area of the sparse backward
 };
 
 StatePtrs state_ptrs(void *state, const StateLayout &L)
@@ -80,7 +79,6 @@ StatePtrs state_ptrs(void *state, const StateLayout &L)
     p.aux = b + L.off_aux;
     p.C = reinterpret_cast<unsigned short *>(b + L.off_cell);
     p.active = reinterpret_cast<unsigned *>(b + L.off_active);
-    p.bwd = reinterpret_cast<unsigned *>(b + L.off_bwd);
     return p;
 }
 
@@ -285,7 +283,7 @@ int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const
 
 template <typename T, bool HAS_DEF, int BX, int BY>
 int launch_bwd_compact(const T *sdf, const T *deform, const Geo &g, T isoT, T padv, T ix, T iy, T iz, const uint4 *E,
-                       const T *gsrc, T *adj_sdf, T *adj_deform, unsigned *work, bool sparse, cudaStream_t st)
+                       const T *gsrc, T *adj_sdf, T *adj_deform, bool sparse, cudaStream_t st)
 {
     static const int smem_pad = env_int("DISO_BWD_SMEM_PAD", 0);   // experiment knob: caps the CTAs per SM
     const size_t smem = bwd_compact_smem<T, HAS_DEF, BX, BY>() + (size_t)smem_pad;
@@ -302,10 +300,13 @@ int launch_bwd_compact(const T *sdf, const T *deform, const Geo &g, T isoT, T pa
         const size_t G = (size_t)g.X * g.Y * g.Z;
         CU_TRY(cudaMemsetAsync(adj_sdf, 0, G * sizeof(T), st));
         if (HAS_DEF) CU_TRY(cudaMemsetAsync(adj_deform, 0, G * 3 * sizeof(T), st));
+        unsigned *work = nullptr;   // private to this call, see launch_bwd2
+        CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&work), ((size_t)nblk + 16) * sizeof(unsigned), st));
         CU_TRY(cudaMemsetAsync(work, 0, 64, st));
         LAUNCH("mc_backward_mark", st, (bwd_mark_kernel<BX, BY><<<cdiv(nblk, 256), 256, 0, st>>>(g, E, ntx, nty, work)));
         const int ctas = (int)std::min<long long>(nblk, (long long)sm_count() * 6);
         LAUNCH("mc_backward", st, kern<<<ctas, BC_THREADS, smem, st>>>(sdf, deform, g, isoT, padv, ix, iy, iz, E, gsrc, adj_sdf, adj_deform, nty, work));
+        CU_TRY(cudaFreeAsync(work, st));
         return DISO_OK;
     }
     auto kern = mc_backward_compact_kernel<T, HAS_DEF, BX, BY>;
@@ -322,7 +323,7 @@ int launch_bwd_compact(const T *sdf, const T *deform, const Geo &g, T isoT, T pa
 // v2 backward from saved edge records (mc_backward_v2.cuh).
 template <typename T, bool HAS_DEF, int GSRC, int BX, int BY>
 int launch_bwd2(const Geo &g, T isoT, T ix, T iy, T iz, const uint4 *E, const T *gsrc, const DmcSrc &dmc, const T *rec,
-                T *adj_sdf, T *adj_deform, unsigned *work, bool sparse, cudaStream_t st)
+                T *adj_sdf, T *adj_deform, bool sparse, cudaStream_t st)
 {
     const char *name = GSRC >= 2 ? "dmc_backward" : "mc_backward";
     // Shared-memory carve-out: the edge pass keeps 8 (MC) / 20 (DMC, fused dual-vertex adjoint) loads per thread in flight and
@@ -341,10 +342,15 @@ int launch_bwd2(const Geo &g, T isoT, T ix, T iy, T iz, const uint4 *E, const T 
         const size_t G = (size_t)g.X * g.Y * g.Z;
         if (adj_sdf) CU_TRY(cudaMemsetAsync(adj_sdf, 0, G * sizeof(T), st));
         if (HAS_DEF && adj_deform) CU_TRY(cudaMemsetAsync(adj_deform, 0, G * 3 * sizeof(T), st));
+        // list of the touched blocks: private to this call (stream-ordered allocation), so backward passes that share one
+        // saved state -- retained graphs, several streams -- never race on it
+        unsigned *work = nullptr;
+        CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&work), ((size_t)nblk + 16) * sizeof(unsigned), st));
         CU_TRY(cudaMemsetAsync(work, 0, 64, st));
         LAUNCH("mc_backward_mark", st, (bwd_mark_kernel<BX, BY><<<cdiv(nblk, 256), 256, 0, st>>>(g, E, ntx, nty, work)));
         const int ctas = (int)std::min<long long>(nblk, (long long)sm_count() * 6);
         LAUNCH(name, st, kern<<<ctas, B2_THREADS, smem, st>>>(g, isoT, ix, iy, iz, E, gsrc, dmc, rec, adj_sdf, adj_deform, nty, work));
+        CU_TRY(cudaFreeAsync(work, st));
         return DISO_OK;
     }
     auto kern = mc_backward2_kernel<T, HAS_DEF, GSRC, BX, BY>;
@@ -375,7 +381,7 @@ int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, co
     if (force >= 0) sparse = force != 0;
     if (rec) {
         DmcSrc dmc{p.S, reinterpret_cast<const uint4 *>(p.aux), p.C};
-#define DISO_B2(HD, K) launch_bwd2<T, HD, K, BWD2_BX, BWD2_BY>(g, isoT, ix, iy, iz, p.E, gsrc, dmc, rec, adj_sdf, HD ? adj_deform : nullptr, p.bwd, sparse, st)
+#define DISO_B2(HD, K) launch_bwd2<T, HD, K, BWD2_BX, BWD2_BY>(g, isoT, ix, iy, iz, p.E, gsrc, dmc, rec, adj_sdf, HD ? adj_deform : nullptr, sparse, st)
         if (deform) {
             switch (gsrc_kind) { case 1: return DISO_B2(true, 1); case 2: return DISO_B2(true, 2); case 3: return DISO_B2(true, 3); default: return DISO_B2(true, 0); }
         }
@@ -387,8 +393,8 @@ int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, co
     if (!adj_sdf || (deform && !adj_deform)) return fail(DISO_E_INVALID, "adj_sdf / adj_deform may only be NULL when edge_rec is given");
     // block shape (common.cuh: BWD_BX x BWD_BY) from sweeps on B200 (512^3 rand-flexi): 4x6 1.70 ms, 3x8 1.71, 4x7 / 4x8 1.73,
     // 8x4 1.76, 6x8 1.82, 2x8 1.90, 4x4 1.92
-    if (deform) return launch_bwd_compact<T, true, BWD_BX, BWD_BY>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, gsrc, adj_sdf, adj_deform, p.bwd, sparse, st);
-    return launch_bwd_compact<T, false, BWD_BX, BWD_BY>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, gsrc, adj_sdf, adj_deform, p.bwd, sparse, st);
+    if (deform) return launch_bwd_compact<T, true, BWD_BX, BWD_BY>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, gsrc, adj_sdf, adj_deform, sparse, st);
+    return launch_bwd_compact<T, false, BWD_BX, BWD_BY>(sdf, deform, g, isoT, padv, ix, iy, iz, p.E, gsrc, adj_sdf, adj_deform, sparse, st);
 }
 
 template <typename T>

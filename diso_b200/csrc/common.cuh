@@ -88,7 +88,6 @@ struct StateLayout {
     size_t off_cell;     // u16 C[(NCH + 8) * 32] per-cell {case index | offset of first triangle / dual vertex << 8}
     size_t off_active;   // u32 active-chunk lists (ascending chunk id): [0, NCH) chunks owning crossing
                          // edges, [NCH, 2 NCH) chunks with faces
-    size_t off_bwd;      // u32 work area of the sparse backward: {count, cursor, pad[14]} + ids of the touched blocks
     size_t total;
     int n_tiles;
     int sign_tail;
@@ -122,10 +121,6 @@ inline StateLayout make_layout(int alg, const Geo &g)
     L.off_active = o;
     o += (size_t)g.NCH * 2 * 4;
     o = align_up(o, 256);
-    L.off_bwd = o;
-    const size_t blocks1 = (size_t)((g.X + BWD_BX - 1) / BWD_BX) * ((g.Y + BWD_BY - 1) / BWD_BY) * g.NC;
-    const size_t blocks2 = (size_t)((g.X + BWD2_BX - 1) / BWD2_BX) * ((g.Y + BWD2_BY - 1) / BWD2_BY) * g.NC;
-    o += ((blocks1 > blocks2 ? blocks1 : blocks2) + 16) * 4;
     L.total = align_up(o, 256);
     return L;
 }

@@ -328,6 +328,10 @@ def extract_slab(alg, sdf_own, deform_own, x_range, X, isovalue=0.0, normalize=T
     triangles, DMC [Q,4] quads; int64) and ``info`` with the global offsets / totals.  The global
     mesh is the rank-order concatenation.  Gradients flow to ``sdf_own`` / ``deform_own`` of every
     rank (halo contributions are exchanged with the neighbours in backward).
+
+    REQUIREMENT: the halo exchange is a collective in BOTH directions.  Every rank must run backward through the
+    ``verts`` it got -- also a rank that owns nothing (its empty ``verts`` stays attached to the exchange for exactly
+    this reason) -- otherwise its neighbours block in the gradient exchange.
     """
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     a, b = x_range

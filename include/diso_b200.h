@@ -136,8 +136,8 @@ int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, in
  * adj_deform [X,Y,Z,3] (NULL iff deform is NULL) are FULLY written (zeros included);
  * accumulation is an atomic-free gather in a fixed order, so results are deterministic.
  * counts_host: as for emit (NULL allowed); on sparse surfaces it selects the zero-fill + touched-block
- * path, which uses a small work area inside `state` (hence not const: do not run two backward
- * passes on the SAME state concurrently on different streams).
+ * path (its block list is a stream-ordered allocation private to the call, so `state` is only read and
+ * several backward passes may share it -- retained graphs, several streams).
  * edge_rec (ABI v3): the buffer the emit call filled, or NULL.  With it the adjoint runs from the saved records
  * (mc_backward_v2.cuh) and either of adj_sdf / adj_deform may be NULL when that gradient is not wanted; without it
  * the kernel re-gathers sdf / deform (mc_backward_compact.cuh) and both outputs are required. */

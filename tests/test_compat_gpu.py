@@ -64,6 +64,20 @@ def test_C_shim_rejects_bad_inputs():
         m.forward(torch.zeros(4, 4, 4, device=DEV, dtype=torch.float64), 0.0)
 
 
+
+
+def test_C_shim_refuses_unpadded_boundary():
+    """The reference's _C level adds no pad; a boundary below iso would give a different (open) mesh there, so the shim
+    refuses instead of silently closing the surface with its virtual shell."""
+    from diso_b200 import _C, DisoB200Error
+    g = syn.random_sdf((8, 9, 10), "dense", 3).to(DEV)          # values in (-0.5, 0.5): the boundary crosses iso = 0
+    with pytest.raises(DisoB200Error, match="padded input"):
+        _C.CUMCFloat().forward(g, 0.0)
+    gp = F.pad(g, (1, 1, 1, 1, 1, 1), "constant", 1.0).contiguous()
+    v, f = _C.CUMCFloat().forward(gp, 0.0)
+    assert v.shape[0] > 0 and f.dtype == torch.int32
+
+
 @pytest.mark.parametrize("alg", ["mc", "dmc"])
 def test_forward_batch_equals_loop(alg):
     import diso_b200

@@ -10,7 +10,7 @@ import torch  # noqa: E402
 
 import diso_b200  # noqa: E402
 from diso_b200 import synthetic as syn  # noqa: E402
-from tests.refload import load_reference  # noqa: E402
+from tests.refload import load_reference  # noqa: E402  (tools may use the test helpers; bench.py does not)
 
 dev = "cuda:0"
 ref = load_reference()
