@@ -39,17 +39,25 @@ for blk, dem in zip(blocks, names):
         if base in ("LDG", "STG", "LDS", "STS") and (".128" in op or ".64" in op):
             mix[base + (".128" if ".128" in op else ".64")] += 1
     rows.append((short, len(ins), mix))
+    # every fp32 kernel, and the fp64 instantiations of the primary flavours (dense tiles / with deform / unfused ids):
+    # BASELINE.json asks for a committed listing of each precision
     is_f32 = "double" not in dem and "debug" not in dem
-    if is_f32:
+    is_f64_primary = "double" in dem and "debug" not in dem and not re.search(r"<double, true>|double, \d, true|double, false, \d", short) \
+        and "queue" not in short
+    if is_f32 or is_f64_primary:
         fn = re.sub(r"[^A-Za-z0-9_]+", "_", short).strip("_") + ".sass"
         with open(os.path.join(a.out, fn), "w") as f:
             f.write("// %s\n// cuobjdump -sass of %s (sm_100a), encodings stripped\n" % (dem, os.path.basename(a.lib)))
             for addr, t in ins:
                 f.write("/*%s*/ %s\n" % (addr, t))
-cols = ["LDG", "LDG.128", "STG", "STG.128", "LDS", "LDS.128", "STS", "STS.128", "LDL", "STL", "POPC", "SHFL", "BAR", "ATOM", "ATOMS", "RED", "MUFU", "DFMA", "HMMA", "UTCHMMA"]
+cols = ["LDG", "LDG.128", "STG", "STG.128", "LDS", "LDS.128", "STS", "STS.128", "LDL", "STL", "POPC", "SHFL", "BAR", "ATOM", "ATOMS", "RED", "MUFU", "FADD2", "DFMA", "HMMA", "UTCHMMA"]
 with open(os.path.join(a.out, "INDEX.md"), "w") as f:
     f.write("# SASS instruction mix per kernel (`tools/dump_sass.py`, static counts)\n\n")
-    f.write("Listings of the fp32 kernels are in this directory (one file per kernel). No kernel uses local memory\n(LDL/STL = 0) or tensor pipes (no dense contraction on this path).\n\n")
+    spill = sorted((short, mix.get("LDL", 0), mix.get("STL", 0)) for short, n, mix in rows if mix.get("LDL", 0) or mix.get("STL", 0))
+    f.write("Listings of every fp32 kernel and of the fp64 instantiations of the primary flavours are in this directory (one file\n"
+            "per kernel). No tensor pipes (no dense contraction on this path); FADD2 = Blackwell's packed f32x2 add (the accumulators\n"
+            "of the saved-record backward).  Local memory: %s.\n\n" % (
+                "none" if not spill else "a few spilled words under the 32-register caps -- " + ", ".join("`%s` LDL %d / STL %d" % t for t in spill)))
     f.write("| kernel | instr | " + " | ".join(cols) + " |\n|---|---|" + "---|" * len(cols) + "\n")
     for short, n, mix in sorted(rows):
         f.write("| `%s` | %d | " % (short, n) + " | ".join(str(mix.get(c, 0)) for c in cols) + " |\n")

@@ -33,6 +33,7 @@ M = [("us", "gpu__time_duration.sum", 1.0), ("inst/chunk", "smsp__inst_executed.
      ("thr/inst", "smsp__thread_inst_executed_per_inst_executed.ratio", 1.0),
      ("issue %", "smsp__issue_active.avg.pct_of_peak_sustained_active", 1.0),
      ("L1 %", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", 1.0),
+     ("LSU wf %", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", 1.0),
      ("L2 %", "lts__throughput.avg.pct_of_peak_sustained_elapsed", 1.0),
      ("DRAM %", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", 1.0),
      ("DRAM rd MB", "dram__bytes_read.sum", 1.0), ("DRAM wr MB", "dram__bytes_write.sum", 1.0),
@@ -56,6 +57,9 @@ for r in data:
         if "bytes" in key:
             u = units[h.index(key)]
             v = v * {"Mbyte": 1.0, "Gbyte": 1000.0, "Kbyte": 0.001, "byte": 1e-6}.get(u, 1.0)
+        if key == "gpu__time_duration.sum":   # ncu picks the unit per column: normalise to microseconds
+            u = units[h.index(key)]
+            v = v * {"us": 1.0, "usecond": 1.0, "ms": 1000.0, "msecond": 1000.0, "ns": 0.001, "nsecond": 0.001, "s": 1e6, "second": 1e6}.get(u, 1.0)
         vals.append("%.1f" % v if abs(v) < 1e5 else "%.3g" % v)
     out.append("| `%s` | " % name[:44] + " | ".join(vals) + " |")
 open(a.out, "w").write("\n".join(out) + "\n")
