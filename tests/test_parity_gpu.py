@@ -50,7 +50,7 @@ def close(a, b, dtype, what):
     a, b = a[fin], b[fin]
     scale = max(1.0, float(np.abs(b).max()) if b.size else 1.0)
     err = float(np.abs(a - b).max()) if a.size else 0.0
-    assert err <= TOL[dtype] * scale * 4, "%s: max err %.3e (scale %.3e)" % (what, err, scale)
+    assert err <= TOL[dtype] * scale, "%s: max err %.3e (scale %.3e)" % (what, err, scale)   # the north-star bar itself (round 1 allowed 4x)
 
 
 F64 = {"sphere32", "rand_flexi_24", "ragged_5x9x70", "ties_int", "iso_0p37", "tiny_2x2x2"}

@@ -41,10 +41,10 @@ def test_sharded_cuda_equals_single_gpu(tmp_path, alg, world, kind, use_def, fie
     assert torch.equal(faces, ef.cpu()), "connectivity of the stitched mesh differs"
     assert torch.equal(verts, ev.detach().cpu()), "stitched vertices are not bit-identical to the single-GPU run"
     gs = s.grad.cpu().numpy()
-    np.testing.assert_allclose(gsdf.numpy(), gs, rtol=0, atol=5e-5 * max(1.0, np.abs(gs).max()))
+    np.testing.assert_allclose(gsdf.numpy(), gs, rtol=0, atol=1e-5 * max(1.0, np.abs(gs).max()))
     if use_def:
         gd = d.grad.cpu().numpy()
-        np.testing.assert_allclose(gdef.numpy(), gd, rtol=0, atol=5e-5 * max(1.0, np.abs(gd).max()))
+        np.testing.assert_allclose(gdef.numpy(), gd, rtol=0, atol=1e-5 * max(1.0, np.abs(gd).max()))
 
 
 @pytest.mark.parametrize("world", [2])
