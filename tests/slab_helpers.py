@@ -109,3 +109,26 @@ def worker(rank, world, port, alg, sdf, deform, iso, normalize, use_cuda, out_di
                    os.path.join(out_dir, "rank%d.pt" % rank))
     finally:
         dist.destroy_process_group()
+
+
+def field_worker(rank, world, port, full, out_dir):
+    """SlabField mechanics on the CPU (gloo): in-place halo refresh and the gradient return of the halo layers."""
+    import torch.distributed as dist
+    from diso_b200 import parallel
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        X = full.shape[0]
+        a, b = parallel.plan_slabs(X, world)[rank]
+        f = parallel.SlabField(full[a:b].clone(), rank, world)
+        f.ext.requires_grad_(True)
+        ext = f.synced()
+        lo = a - f.n_lo
+        assert torch.equal(ext.detach(), full[lo: b + f.n_hi]), "halo layers differ from the neighbours' layers"
+        # a loss that touches every layer of the extended slab with a global-position-dependent weight
+        w = torch.arange(lo, b + f.n_hi, dtype=full.dtype).view(-1, *([1] * (full.dim() - 1))) + 1.0
+        (ext * ext * w).sum().backward()
+        g = f.ext.grad
+        assert float(g[: f.n_lo].abs().sum()) == 0 and float(g[f.n_lo + f.n:].abs().sum()) == 0, "halo gradients must be returned, not kept"
+        torch.save(dict(a=a, b=b, grad=g[f.n_lo: f.n_lo + f.n].clone()), os.path.join(out_dir, "field%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()

@@ -12,7 +12,7 @@ import torch
 import torch.multiprocessing as mp
 
 from diso_b200 import parallel, synthetic as syn
-from tests.slab_helpers import worker
+from tests.slab_helpers import field_worker, worker
 
 
 def _port():
@@ -46,6 +46,29 @@ def test_plan_slabs():
     assert parallel.plan_slabs(1024, 8)[-1] == (896, 1024)
     with pytest.raises(ValueError):
         parallel.plan_slabs(3, 2)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_field_halo_refresh_and_gradient_return(tmp_path, world):
+    """parallel.SlabField on the CPU (gloo): halos are filled in place from the neighbours, and in backward the gradients
+    that land on halo layers are sent to their owners and added there -- every layer of the grid ends up with the
+    gradient contributions of ALL ranks that looked at it."""
+    X = 11
+    full = torch.arange(X * 3 * 4, dtype=torch.float64).reshape(X, 3, 4) / 7.0
+    mp.spawn(field_worker, args=(world, _port(), full, str(tmp_path)), nprocs=world, join=True)
+    grad = torch.zeros_like(full)
+    for r in range(world):
+        p = torch.load(tmp_path / ("field%d.pt" % r), weights_only=False)
+        grad[p["a"]: p["b"]] = p["grad"]
+    # expected: layer x is seen by its owner and by every neighbour whose halo covers it; each contributes 2 v (x + 1)
+    slabs = parallel.plan_slabs(X, world)
+    seen = torch.zeros(X)
+    for r, (a, b) in enumerate(slabs):
+        lo = a - (parallel.HALO if r > 0 else 0)
+        hi = b + (parallel.HALO if r < world - 1 else 0)
+        seen[lo:hi] += 1
+    want = 2 * full * (torch.arange(X, dtype=torch.float64) + 1.0).view(-1, 1, 1) * seen.view(-1, 1, 1).double()
+    assert torch.allclose(grad, want, rtol=1e-13, atol=0)
 
 
 CASES = [("mc", 2, True), ("dmc", 2, True), ("mc", 3, False), ("dmc", 3, True)]
