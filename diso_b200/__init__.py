@@ -115,9 +115,11 @@ class _Extract(Function):
     keeps batch / activation-checkpoint semantics (nothing lives in the extractor object)."""
 
     @staticmethod
-    def forward(ctx, grid, deform, alg, isovalue, normalize, grad_mode, state, counts, frame=None):
+    def forward(ctx, grid, deform, alg, isovalue, normalize, grad_mode, state, counts, frame=None, aux=None):
         # frame: None, or (x_origin, X_global, id_offset) when `grid` is a slab of a larger grid
         # (diso_b200/parallel.py): vertices come out in the global frame, faces with global ids
+        # aux: None, or a dict that receives side outputs; aux["want_quad_flags"] makes the DMC quad kernel decide every
+        # quad's diagonal for the triangle split (aux["quad_flags"], one byte per quad) while its four ids are in registers
         L = _lib.load()
         ctx.frame = _lib.Frame(*[int(v) for v in frame]) if frame is not None else None
         X, Y, Z = grid.shape
@@ -137,8 +139,11 @@ class _Extract(Function):
             _lib.check(L.diso_b200_mc_emit(*args, verts.data_ptr(), faces.data_ptr(), _ptr(rec), max(n_edges, 1), _stream()))
         else:
             scratch = torch.empty((max(n_faces, 1), 3), dtype=grid.dtype, device=grid.device)  # edge crossings
+            qflags = None
+            if aux is not None and aux.get("want_quad_flags"):
+                qflags = aux["quad_flags"] = torch.empty(max(n_faces, 1), dtype=torch.uint8, device=grid.device)
             _lib.check(L.diso_b200_dmc_emit(*args, scratch.data_ptr(), verts.data_ptr(), faces.data_ptr(), _ptr(rec),
-                                            max(n_edges, 1), _stream()))
+                                            max(n_edges, 1), _ptr(qflags), _stream()))
         ctx.alg, ctx.isovalue, ctx.normalize, ctx.grad_mode = alg, float(isovalue), bool(normalize), grad_mode
         ctx.n_edges = n_edges
         ctx.has_rec = rec is not None
@@ -161,9 +166,9 @@ class _Extract(Function):
         X, Y, Z = grid.shape
         need_grid = ctx.needs_input_grad[0]
         need_deform = deform is not None and ctx.needs_input_grad[1]
-        none7 = (None,) * 7
+        rest = (None,) * 8   # alg, isovalue, normalize, grad_mode, state, counts, frame, aux
         if adj_verts is None:  # verts did not take part in the loss: all gradients are zero
-            return (torch.zeros_like(grid) if need_grid else None, torch.zeros_like(deform) if need_deform else None) + none7
+            return (torch.zeros_like(grid) if need_grid else None, torch.zeros_like(deform) if need_deform else None) + rest
         # the reference requires a contiguous adj_verts and raises otherwise (pybind.cpp:142);
         # expanded gradients (e.g. from verts.sum() with normalize=False) are made contiguous here.
         adj_verts = adj_verts.contiguous()
@@ -190,10 +195,10 @@ class _Extract(Function):
                                                     adj_verts.data_ptr(), int(ctx.normalize), _lib.frame_ptr(ctx.frame),
                                                     ctx.grad_mode, _ptr(rec), max(ctx.n_edges, 1), _ptr(scratch),
                                                     _ptr(adj_grid), _ptr(adj_deform), _stream()))
-        return (adj_grid if need_grid else None, adj_deform if need_deform else None) + none7
+        return (adj_grid if need_grid else None, adj_deform if need_deform else None) + rest
 
 
-def _run(alg, dtype, grad_mode, grid, deform, isovalue, normalize, want_state=False, slab_mode=False):
+def _run(alg, dtype, grad_mode, grid, deform, isovalue, normalize, want_state=False, slab_mode=False, aux=None):
     _check_inputs(grid, deform, dtype)
     k = 3 if alg == _lib.ALG_MC else 4
     with _on(grid.device):
@@ -211,7 +216,7 @@ def _run(alg, dtype, grad_mode, grid, deform, isovalue, normalize, want_state=Fa
             return out + (None,) if want_state else out
         if max(n_verts, n_faces) >= 2 ** 32 - 1:
             raise DisoB200Error("mesh too large for one call (%d verts, %d faces): shard the grid" % (n_verts, n_faces))
-        out = _Extract.apply(g, d, alg, float(isovalue), bool(normalize), grad_mode, state, counts)
+        out = _Extract.apply(g, d, alg, float(isovalue), bool(normalize), grad_mode, state, counts, None, aux)
         return out + (state,) if want_state else out
 
 
@@ -327,11 +332,12 @@ class DiffDMC(nn.Module):
         _lib.load()
 
     def forward(self, grid, deform=None, isovalue=0.0, return_quads=False, normalize=True):
-        verts, quads = _run(_lib.ALG_DMC, self.dtype, _grad_mode(self.grad_mode), grid, deform, isovalue, normalize)
+        aux = None if (return_quads or os.environ.get("DISO_B200_NO_QUAD_FLAGS")) else {"want_quad_flags": True}
+        verts, quads = _run(_lib.ALG_DMC, self.dtype, _grad_mode(self.grad_mode), grid, deform, isovalue, normalize, aux=aux)
         if return_quads or quads.shape[0] == 0:
             # (the reference's early-out returns the (0,4) int32 tensor even when triangles were asked for)
             return verts, quads
-        return verts, split_quads(verts.detach(), quads)
+        return verts, split_quads(verts.detach(), quads, aux.get("quad_flags") if aux else None)
 
     def forward_batch(self, grids, deforms=None, isovalue=0.0, return_quads=False, normalize=True):
         """List of (verts, faces), one per shape, with a single host synchronisation for the batch."""
@@ -341,9 +347,10 @@ class DiffDMC(nn.Module):
         return [(v, q if q.shape[0] == 0 else split_quads(v.detach(), q)) for v, q in res]
 
 
-def split_quads(verts, quads):
+def split_quads(verts, quads, quad_flags=None):
     """Quad -> triangle split of diso/__init__.py:118-147 (max-min-angle diagonal, config-1 quads
-    first) as one fused CUDA pass.  verts [V,3] float32/64, quads [Q,4] int64 -> faces [2Q,3] int64."""
+    first) as one fused CUDA pass.  verts [V,3] float32/64, quads [Q,4] int64 -> faces [2Q,3] int64.
+    quad_flags: the per-quad diagonal flags the DMC emit already computed (DiffDMC's default path), or None."""
     L = _lib.load()
     verts = verts.contiguous()
     quads = quads.contiguous()
@@ -353,7 +360,7 @@ def split_quads(verts, quads):
         return faces
     with torch.cuda.device(quads.device):
         scratch = torch.empty(L.diso_b200_quad_split_scratch_bytes(nq), dtype=torch.uint8, device=quads.device)
-        _lib.check(L.diso_b200_quad_split(verts.data_ptr(), _DTYPES[verts.dtype], quads.data_ptr(), nq,
+        _lib.check(L.diso_b200_quad_split(verts.data_ptr(), _DTYPES[verts.dtype], quads.data_ptr(), nq, _ptr(quad_flags),
                                           scratch.data_ptr(), faces.data_ptr(), _stream()))
     return faces
 

@@ -42,11 +42,11 @@ SIGNATURES = {
     "diso_b200_count": (_i, [_i, _vp, _i, _i, _i, _i, _d, _vp, _sz, _vp]),
     "diso_b200_read_counts": (_i, [_vp, _vp, _vp]),
     "diso_b200_mc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _vp]),
-    "diso_b200_dmc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "diso_b200_dmc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "diso_b200_mc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
     "diso_b200_dmc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _i, _vp, _i, _vp, _i64, _vp, _vp, _vp, _vp]),
     "diso_b200_quad_split_scratch_bytes": (_sz, [_i64]),
-    "diso_b200_quad_split": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp]),
+    "diso_b200_quad_split": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp, _vp]),
     "diso_b200_debug_cell_codes": (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
     "diso_b200_launch_count": (ctypes.c_longlong, []),
     "diso_b200_profile_enable": (_i, [_i]),

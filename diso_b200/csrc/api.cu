@@ -252,7 +252,7 @@ int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const 
 
 template <typename T>
 int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const int64_t *counts_host,
-                  int normalize, const Frame &fr, T *scratch, T *verts, long long *quads, T *rec, cudaStream_t st)
+                  int normalize, const Frame &fr, T *scratch, T *verts, long long *quads, T *rec, unsigned char *qflags, cudaStream_t st)
 {
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
@@ -273,9 +273,14 @@ int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const
         else LAUNCH("dmc_emit_verts", st, (dmc_dual_verts_kernel<T, false><<<tc.ctas, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, tc.list, tc.n_active, verts)));
     }
     if (te.ctas) {
-#define DISO_QUADS(LISTED, OFFSET) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, LISTED, OFFSET><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, fr.id_offset, quads, nullptr, 0)))
-        if (fr.id_offset != 0) { if (te.list) DISO_QUADS(true, true); else DISO_QUADS(false, true); }
-        else                   { if (te.list) DISO_QUADS(true, false); else DISO_QUADS(false, false); }
+#define DISO_QUADS(LISTED, OFFSET, DIAG) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, LISTED, OFFSET, DIAG><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, fr.id_offset, quads, nullptr, 0, verts, qflags)))
+        if (qflags) {
+            if (fr.id_offset != 0) { if (te.list) DISO_QUADS(true, true, true); else DISO_QUADS(false, true, true); }
+            else                   { if (te.list) DISO_QUADS(true, false, true); else DISO_QUADS(false, false, true); }
+        } else {
+            if (fr.id_offset != 0) { if (te.list) DISO_QUADS(true, true, false); else DISO_QUADS(false, true, false); }
+            else                   { if (te.list) DISO_QUADS(true, false, false); else DISO_QUADS(false, false, false); }
+        }
 #undef DISO_QUADS
     }
     return DISO_OK;
@@ -532,7 +537,8 @@ int diso_b200_mc_emit(const void *sdf, const void *deform, int dtype, int X, int
 
 int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
                        const void *state, const int64_t *counts_host, int normalize, const diso_b200_frame *frame,
-                       void *scratch, void *verts, int64_t *quads, void *edge_rec, int64_t edge_rec_stride, void *stream)
+                       void *scratch, void *verts, int64_t *quads, void *edge_rec, int64_t edge_rec_stride, uint8_t *quad_flags,
+                       void *stream)
 {
     int rc = check_dims(DISO_ALG_DMC, dtype, X, Y, Z);
     if (rc) return rc;
@@ -544,9 +550,9 @@ int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == DISO_F32)
         return dmc_emit_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, counts_host, normalize, fr,
-                                    static_cast<float *>(scratch), static_cast<float *>(verts), reinterpret_cast<long long *>(quads), static_cast<float *>(edge_rec), st);
+                                    static_cast<float *>(scratch), static_cast<float *>(verts), reinterpret_cast<long long *>(quads), static_cast<float *>(edge_rec), quad_flags, st);
     return dmc_emit_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, counts_host, normalize, fr,
-                                 static_cast<double *>(scratch), static_cast<double *>(verts), reinterpret_cast<long long *>(quads), static_cast<double *>(edge_rec), st);
+                                 static_cast<double *>(scratch), static_cast<double *>(verts), reinterpret_cast<long long *>(quads), static_cast<double *>(edge_rec), quad_flags, st);
 }
 
 int diso_b200_mc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
@@ -624,14 +630,14 @@ size_t diso_b200_quad_split_scratch_bytes(int64_t n_quads)
     return quad_scratch_layout(n_quads).total;
 }
 
-int diso_b200_quad_split(const void *verts, int dtype, const int64_t *quads, int64_t n_quads, void *scratch,
+int diso_b200_quad_split(const void *verts, int dtype, const int64_t *quads, int64_t n_quads, const uint8_t *quad_flags, void *scratch,
                          int64_t *faces, void *stream)
 {
     if (dtype != DISO_F32 && dtype != DISO_F64) return fail(DISO_E_INVALID, "unknown dtype %d", dtype);
     if (n_quads < 0) return fail(DISO_E_INVALID, "negative n_quads");
     if (n_quads == 0) return DISO_OK;
     if (n_quads >= (1ll << 32) - 1) return fail(DISO_E_TOOLARGE, "too many quads for one call");
-    if (!verts || !quads || !scratch || !faces) return fail(DISO_E_INVALID, "null pointer");
+    if ((!verts && !quad_flags) || !quads || !scratch || !faces) return fail(DISO_E_INVALID, "null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int tiles = cdiv(n_quads, QS_TILE);
     const QuadScratch L = quad_scratch_layout(n_quads);
@@ -643,8 +649,15 @@ int diso_b200_quad_split(const void *verts, int dtype, const int64_t *quads, int
     unsigned char *flags = reinterpret_cast<unsigned char *>(b + L.off_flags);
     const long long *qd = reinterpret_cast<const long long *>(quads);
     CU_TRY(cudaMemsetAsync(b, 0, L.off_tile, st));   // total, ticket, tile descriptors
-    if (dtype == DISO_F32) LAUNCH("quad_diag", st, quad_diag_kernel<float><<<tiles, QS_THREADS, 0, st>>>(static_cast<const float *>(verts), qd, n_quads, flags, tile_off, desc, ticket, total));
-    else LAUNCH("quad_diag", st, quad_diag_kernel<double><<<tiles, QS_THREADS, 0, st>>>(static_cast<const double *>(verts), qd, n_quads, flags, tile_off, desc, ticket, total));
+    if (quad_flags) {
+        // the diagonal of every quad was decided by dmc_emit_quads: only the scan of the flag bytes is left
+        flags = const_cast<unsigned char *>(quad_flags);
+        LAUNCH("quad_scan", st, (quad_scan_kernel<<<cdiv(n_quads, QSC_TILE), QS_THREADS, 0, st>>>(flags, n_quads, tile_off, desc, ticket, total)));
+    } else if (dtype == DISO_F32) {
+        LAUNCH("quad_diag", st, (quad_diag_kernel<float><<<tiles, QS_THREADS, 0, st>>>(static_cast<const float *>(verts), qd, n_quads, flags, tile_off, desc, ticket, total)));
+    } else {
+        LAUNCH("quad_diag", st, (quad_diag_kernel<double><<<tiles, QS_THREADS, 0, st>>>(static_cast<const double *>(verts), qd, n_quads, flags, tile_off, desc, ticket, total)));
+    }
     LAUNCH("quad_emit", st, quad_emit_kernel<<<tiles, QS_THREADS, 0, st>>>(qd, n_quads, flags, tile_off, total, reinterpret_cast<long long *>(faces)));
     return DISO_OK;
 }

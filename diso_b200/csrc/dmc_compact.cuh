@@ -10,6 +10,7 @@
 // classify_scan, instead of being re-derived from 8 sign words 7 times per grid point.
 #pragma once
 #include "compact.cuh"
+#include "quad_split.cuh"
 #include "tables.cuh"
 
 namespace diso {
@@ -17,13 +18,18 @@ namespace diso {
 // MODE 0: quads.  MODE 1: exact adjoint.  MODE 2: reference-compatible adjoint (every patch of a
 // cell reads the adjoint of the cell's FIRST dual vertex, cudualmc.cu:975,990).
 // OFFSET (MODE 0 only): add id_offset to every index (slab -> global ids).
-template <typename T, int MODE, bool LISTED, bool OFFSET = false>
+// DIAG (MODE 0 only): also decide the quad's diagonal for the quad -> triangle split (diso/__init__.py:118-147) while its
+// four dual-vertex ids are in registers: gathers the four (final, API-frame) vertices written by dmc_dual_verts and
+// stores one flag byte per quad; DiffDMC's default path then needs only a scan over those bytes (quad_diag<PRECOMPUTED>)
+// instead of re-reading the 32-byte quads and chasing ids -> vertices (2.15 ms at 512^3, latency-bound).
+template <typename T, int MODE, bool LISTED, bool OFFSET = false, bool DIAG = false>
 __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const unsigned *__restrict__ S,
                                                               const uint4 *__restrict__ E, const uint4 *__restrict__ P,
                                                               const unsigned short *__restrict__ C,
                                                               const unsigned *__restrict__ alist, int n_active, T ix, T iy, T iz,
                                                               const T *__restrict__ adj_dual, long long id_offset,
-                                                              long long *__restrict__ quads, T *__restrict__ gedge, int gedge_soa)
+                                                              long long *__restrict__ quads, T *__restrict__ gedge, int gedge_soa,
+                                                              const T *__restrict__ verts = nullptr, unsigned char *__restrict__ qflags = nullptr)
 {
     __shared__ unsigned short s_list[CT_MAX_EDGES];
     __shared__ unsigned s_case[256];
@@ -75,6 +81,15 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
         }
         const size_t rank = (size_t)tile_base + i;
         if (MODE == 0) {
+            if (DIAG) {   // local ids index the local vertex array (the slab offset is added below)
+                Vec3<T> v[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const T *pv = verts + id[c] * 3;
+                    v[c] = Vec3<T>{__ldg(pv), __ldg(pv + 1), __ldg(pv + 2)};
+                }
+                qflags[rank] = quad_first_diagonal(v[0], v[1], v[2], v[3]) ? 1 : 0;
+            }
             if (OFFSET) { id[0] += id_offset; id[1] += id_offset; id[2] += id_offset; id[3] += id_offset; }
             longlong2 *dst = reinterpret_cast<longlong2 *>(quads + rank * 4);
             __stcs(dst, make_longlong2(id[0], id[1]));

@@ -55,7 +55,23 @@ struct __align__(16) QuadTileDesc {
     unsigned long long incl;
 };
 
+// The reference's choice for one quad (diso/__init__.py:118-147): true = config 1 ([0,1,3],[1,2,3]), i.e. angles1 < angles2.
+template <typename T>
+__device__ __forceinline__ bool quad_first_diagonal(const Vec3<T> &v0, const Vec3<T> &v1, const Vec3<T> &v2, const Vec3<T> &v3)
+{
+    const Vec3<T> S0 = unit(v1, v0), S1 = unit(v2, v1), S2 = unit(v3, v2), S3 = unit(v0, v3);
+    const Vec3<T> D0 = unit(v2, v0), D1 = unit(v3, v1);
+    const T t13a = max3(-dot3(S0, S3), -dot3(D1, S0), -dot3(S3, D1));
+    const T t13b = max3(dot3(S1, D1), -dot3(S2, S1), dot3(D1, S2));
+    const T t02a = max3(dot3(S0, D0), -dot3(S1, S0), dot3(D0, S1));
+    const T t02b = max3(-dot3(D0, S3), -dot3(S2, D0), -dot3(S3, S2));
+    const T a1 = t13a > t13b ? t13a : t13b;
+    const T a2 = t02a > t02b ? t02a : t02b;
+    return a1 < a2;
+}
+
 // Q1: diagonal choice + exclusive prefix of the config-1 counts in one pass.
+// (When dmc_emit_quads already wrote the flags -- DiffDMC's default path -- quad_scan_kernel below replaces this kernel.)
 //
 // The reference evaluates 4 triangles x 3 angles, each from two freshly normalised edge vectors
 // (24 normalisations: 24 square roots, 72 divisions per quad).  Only six distinct directions exist -- the
@@ -107,15 +123,7 @@ __global__ void __launch_bounds__(QS_THREADS, sizeof(T) == 4 ? 8 : 3) quad_diag_
 #pragma unroll
     for (int i = 0; i < QS_PER; ++i) {
         const long long q = q0 + (long long)i * QS_THREADS;
-        const Vec3<T> S0 = unit(v[i][1], v[i][0]), S1 = unit(v[i][2], v[i][1]), S2 = unit(v[i][3], v[i][2]), S3 = unit(v[i][0], v[i][3]);
-        const Vec3<T> D0 = unit(v[i][2], v[i][0]), D1 = unit(v[i][3], v[i][1]);
-        const T t13a = max3(-dot3(S0, S3), -dot3(D1, S0), -dot3(S3, D1));
-        const T t13b = max3(dot3(S1, D1), -dot3(S2, S1), dot3(D1, S2));
-        const T t02a = max3(dot3(S0, D0), -dot3(S1, S0), dot3(D0, S1));
-        const T t02b = max3(-dot3(D0, S3), -dot3(S2, D0), -dot3(S3, S2));
-        const T a1 = t13a > t13b ? t13a : t13b;
-        const T a2 = t02a > t02b ? t02a : t02b;
-        const bool f = q < nq && a1 < a2;
+        const bool f = q < nq && quad_first_diagonal(v[i][0], v[i][1], v[i][2], v[i][3]);
         if (q < nq) flags[q] = f ? 1 : 0;
         mine += f ? 1u : 0u;
     }
@@ -155,6 +163,80 @@ __global__ void __launch_bounds__(QS_THREADS, sizeof(T) == 4 ? 8 : 3) quad_diag_
             tile_off[tile] = (unsigned)excl;   // < 2^32: callers cap n_quads
             if ((long long)(tile + 1) * QS_TILE >= nq) *total = excl + cnt;   // last tile: number of config-1 quads
         }
+    }
+}
+
+// Q1': the scan alone, for flags that dmc_emit_quads already wrote (DiffDMC's default path).  A CTA owns 4096 quads
+// (one 128-bit load of 16 flag bytes per thread) = 16 of quad_emit's 256-quad tiles, so the ticket / look-back
+// machinery runs 16x less often than in quad_diag (283 k tiles at 512^3 cost 1.18 ms when nothing hides them).
+constexpr int QSC_PER = 16;
+constexpr int QSC_TILE = QS_THREADS * QSC_PER;
+static_assert(QS_TILE == 16 * QSC_PER && QS_PER == 1, "16 threads of the scan cover one emit tile");
+
+__global__ void __launch_bounds__(QS_THREADS) quad_scan_kernel(const unsigned char *__restrict__ flags, long long nq,
+                                                             unsigned *__restrict__ tile_off, QuadTileDesc *__restrict__ desc,
+                                                             unsigned *__restrict__ ticket, unsigned long long *__restrict__ total)
+{
+    __shared__ unsigned s_tile;
+    __shared__ unsigned s_warp[QS_THREADS / 32];
+    __shared__ unsigned long long s_excl;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const long long q0 = (long long)tile * QSC_TILE + (long long)tid * QSC_PER;
+    unsigned c = 0;
+    if (q0 + QSC_PER <= nq) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(flags + q0));
+        c = __popc(w.x & 0x01010101u) + __popc(w.y & 0x01010101u) + __popc(w.z & 0x01010101u) + __popc(w.w & 0x01010101u);
+    } else {
+        for (long long q = q0; q < nq; ++q) c += flags[q] != 0;
+    }
+    unsigned inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const unsigned t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    unsigned before = inc - c, cnt = 0;
+#pragma unroll
+    for (int w = 0; w < QS_THREADS / 32; ++w) { const unsigned t = s_warp[w]; if (w < wid) before += t; cnt += t; }
+    // ---- decoupled look-back over the 4096-quad tiles (warp 0), same protocol as quad_diag ----------------------
+    if (tid < 32) {
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            if (lane == 0) { st_relaxed_u64(&desc[0].incl, cnt); st_release_u32(&desc[0].flag, 2u); }
+        } else {
+            if (lane == 0) { desc[tile].agg = cnt; st_release_u32(&desc[tile].flag, 1u); }
+            int base = (int)tile - 1;
+            while (true) {
+                const int t = base - lane;
+                unsigned fl = 2u;
+                unsigned long long x = 0;
+                if (t >= 0) {
+                    do { fl = ld_acquire_u32(&desc[t].flag); } while (fl == 0u);
+                    x = fl == 2u ? ld_relaxed_u64(&desc[t].incl) : (unsigned long long)*reinterpret_cast<volatile unsigned *>(&desc[t].agg);
+                }
+                const unsigned m = __ballot_sync(FULL, fl == 2u);
+                const int stop = m ? (__ffs(m) - 1) : 32;
+                if (lane > stop) x = 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(FULL, x, d);
+                excl += x;
+                if (m) break;
+                base -= 32;
+            }
+            if (lane == 0) { st_relaxed_u64(&desc[tile].incl, excl + cnt); st_release_u32(&desc[tile].flag, 2u); }
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if ((long long)(tile + 1) * QSC_TILE >= nq) *total = excl + cnt;   // last tile: number of config-1 quads
+        }
+    }
+    __syncthreads();
+    // thread 16 s starts emit tile 16 tile + s
+    if ((tid & 15) == 0) {
+        const long long et = (long long)tile * 16 + (tid >> 4);
+        if (et * QS_TILE < nq) tile_off[et] = (unsigned)(s_excl + before);
     }
 }
 

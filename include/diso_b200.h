@@ -124,11 +124,14 @@ int diso_b200_mc_emit(const void *sdf, const void *deform, int dtype, int X, int
  * cudualmc.cu:907-955, 1027-1056, and diso/__init__.py:110-116).
  * verts: [n_verts,3] dtype; quads: [n_quads,4] int64.
  * scratch: caller-owned, n_quads*3 elements of dtype (edge crossings, each evaluated once).
- * edge_rec / edge_rec_stride: as for diso_b200_mc_emit (the crossing edges are the quads). */
+ * edge_rec / edge_rec_stride: as for diso_b200_mc_emit (the crossing edges are the quads).
+ * quad_flags (may be NULL): [n_quads] bytes; when given, the quad kernel also decides each quad's diagonal for the
+ * quad -> triangle split (1 = first diagonal, [0,1,3][1,2,3]) while the four ids are in registers; pass the buffer to
+ * diso_b200_quad_split, which then only scans the bytes. */
 int diso_b200_dmc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
                        double iso, const void *state, const int64_t *counts_host, int normalize,
                        const diso_b200_frame *frame, void *scratch, void *verts, int64_t *quads,
-                       void *edge_rec, int64_t edge_rec_stride, void *stream);
+                       void *edge_rec, int64_t edge_rec_stride, uint8_t *quad_flags, void *stream);
 
 /* Backward, marching cubes (replaces adj_create_cell_mc_verts, cumc.cu:474-512, the dense
  * zero-fills of diso/__init__.py:33,40 and the pad-backward slices).  adj_verts is dL/dverts in
@@ -160,10 +163,11 @@ int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X
  * temporaries).  verts [n_verts,3] dtype (API frame), quads [n_quads,4] int64, faces
  * [2*n_quads,3] int64.  scratch: caller-owned, diso_b200_quad_split_scratch_bytes(n_quads).
  * Output order == the reference's mask + cat: all quads whose first diagonal wins
- * (angles1 < angles2 -> [0,1,3],[1,2,3]) in quad order, then the rest ([0,1,2],[0,2,3]). */
+ * (angles1 < angles2 -> [0,1,3],[1,2,3]) in quad order, then the rest ([0,1,2],[0,2,3]).
+ * quad_flags: NULL, or the per-quad flags diso_b200_dmc_emit wrote (then verts may be NULL: nothing is re-read). */
 size_t diso_b200_quad_split_scratch_bytes(int64_t n_quads);
 int diso_b200_quad_split(const void *verts, int dtype, const int64_t *quads, int64_t n_quads,
-                         void *scratch, int64_t *faces, void *stream);
+                         const uint8_t *quad_flags, void *scratch, int64_t *faces, void *stream);
 
 /* Tracing (the reference has none).  diso_b200_launch_count: number of
  * kernels this library has launched in the process.  diso_b200_profile_enable(1) makes every

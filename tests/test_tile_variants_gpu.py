@@ -67,7 +67,7 @@ def test_dense_and_listed_tiles_agree(alg, dtype):
                 grads += [adj_s.clone(), adj_d.clone()]
             else:
                 scratch = torch.empty(((ne + 31) // 32 * 32, 3), dtype=dtype, device=DEV)
-                _lib.check(L.diso_b200_dmc_emit(*common, ch, 1, None, scratch.data_ptr(), verts.data_ptr(), faces.data_ptr(), rp, ne, st))
+                _lib.check(L.diso_b200_dmc_emit(*common, ch, 1, None, scratch.data_ptr(), verts.data_ptr(), faces.data_ptr(), rp, ne, None, st))
                 for gm in (_lib.GRAD_REFERENCE, _lib.GRAD_EXACT):
                     _lib.check(L.diso_b200_dmc_backward(*common, ch, w.data_ptr(), 1, None, gm, rp, ne, scratch.data_ptr(), adj_s.data_ptr(), adj_d.data_ptr(), st))
                     grads += [adj_s.clone(), adj_d.clone()]
