@@ -272,7 +272,10 @@ __device__ __forceinline__ bool dmc_flip(const unsigned *__restrict__ S, const G
 // K2: fused count + decoupled look-back scan.  Thread t of tile T owns chunk k = 256*T + t.
 // ------------------------------------------------------------------------------------------
 template <int ALG>
-__global__ void __launch_bounds__(SCAN_TILE, 8)   // 32 registers: 8 CTAs/SM hide the look-back latency (DMC 0.44 -> 0.42 ms)
+#ifndef DISO_CLASSIFY_MINB
+#define DISO_CLASSIFY_MINB 8
+#endif
+__global__ void __launch_bounds__(SCAN_TILE, DISO_CLASSIFY_MINB)   // 32 registers: 8 CTAs/SM hide the look-back latency (DMC 0.44 -> 0.42 ms)
  classify_scan_kernel(Geo g, const unsigned *__restrict__ S,
                                                                   uint4 *__restrict__ E, void *__restrict__ aux,
                                                                   unsigned short *__restrict__ C,

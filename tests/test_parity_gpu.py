@@ -159,6 +159,42 @@ def test_dmc_triangles_default_path(oracle):
         assert np.array_equal(f.cpu().numpy(), ef), "quad split differs from the numpy restatement"
 
 
+@pytest.mark.parametrize("alg", ["mc", "dmc"])
+def test_gradient_of_one_input_only(alg):
+    """Only the inputs that require a gradient get one (ctx.needs_input_grad): the backward kernel skips the other
+    output entirely (NULL pointer in the C ABI), and the gradient that IS computed equals the one of the full run."""
+    import diso_b200
+    sdf, deform, iso = cases.make("rand_flexi_24")
+    mod = diso_b200.DiffMC() if alg == "mc" else diso_b200.DiffDMC()
+    kw = {} if alg == "mc" else dict(return_quads=True)
+
+    def grads(req_s, req_d):
+        s = sdf.to(DEV).requires_grad_(req_s)
+        d = deform.to(DEV).requires_grad_(req_d)
+        v, _ = mod(s, d, iso, **kw)
+        (v * weights(v.shape[0], v.dtype, DEV)).sum().backward()
+        return s.grad, d.grad
+    gs, gd = grads(True, True)
+    gs1, gd1 = grads(True, False)
+    gs2, gd2 = grads(False, True)
+    assert gd1 is None and gs2 is None
+    assert torch.equal(gs, gs1) and torch.equal(gd, gd2)
+    # retained graph: a second backward over the same forward (the saved state / edge records are only read)
+    s = sdf.to(DEV).requires_grad_(True)
+    d = deform.to(DEV).requires_grad_(True)
+    v, _ = mod(s, d, iso, **kw)
+    loss = (v * weights(v.shape[0], v.dtype, DEV)).sum()
+    loss.backward(retain_graph=True)
+    g1 = s.grad.clone()
+    s.grad = None
+    loss.backward()
+    assert torch.equal(g1, s.grad)
+    # forward-only calls keep no edge records
+    with torch.no_grad():
+        v2, _ = mod(sdf.to(DEV), deform.to(DEV), iso, **kw)
+    assert torch.equal(v2, v.detach())
+
+
 def test_noncontiguous_inputs_and_expanded_grad():
     import diso_b200
     sdf, deform, iso = cases.make("rand_flexi_24")
