@@ -162,6 +162,39 @@ inline void kernel_attrs(const void *fn, const char *env, int carveout_pct, size
 
 constexpr size_t MAX_OPTIN_SMEM = 227 * 1024;   // sm_100: 227 KB per CTA
 
+// Stream-ordered scratch for lists that are private to one call (the sparse backward's touched-block list): a memory pool
+// per device that KEEPS its memory across synchronisations.  (The device's default pool releases everything whenever the
+// stream synchronises -- release threshold 0 -- so every call would pay a fresh cudaMalloc: measured 1.14 -> 3.84 ms for the
+// sphere 512^3 step.)  Returns nullptr on failure with the error recorded.
+inline cudaMemPool_t call_pool()
+{
+    static std::mutex mu;
+    static std::map<int, cudaMemPool_t> pools;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = pools.find(dev);
+    if (it != pools.end()) return it->second;
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    pools[dev] = pool;
+    return pool;
+}
+
+inline cudaError_t call_scratch(void **ptr, size_t bytes, cudaStream_t st)
+{
+    cudaMemPool_t pool = call_pool();
+    if (!pool) return cudaMallocAsync(ptr, bytes, st);
+    return cudaMallocFromPoolAsync(ptr, bytes, pool, st);
+}
+
 // ---- tracing: launch counter + optional per-kernel CUDA-event timing (per host thread) --------
 std::atomic<long long> g_launches{0};
 struct ProfRec { const char *name; cudaEvent_t a, b; };
@@ -306,7 +339,7 @@ int launch_bwd_compact(const T *sdf, const T *deform, const Geo &g, T isoT, T pa
         CU_TRY(cudaMemsetAsync(adj_sdf, 0, G * sizeof(T), st));
         if (HAS_DEF) CU_TRY(cudaMemsetAsync(adj_deform, 0, G * 3 * sizeof(T), st));
         unsigned *work = nullptr;   // private to this call, see launch_bwd2
-        CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&work), ((size_t)nblk + 16) * sizeof(unsigned), st));
+        CU_TRY(call_scratch(reinterpret_cast<void **>(&work), ((size_t)nblk + 16) * sizeof(unsigned), st));
         CU_TRY(cudaMemsetAsync(work, 0, 64, st));
         LAUNCH("mc_backward_mark", st, (bwd_mark_kernel<BX, BY><<<cdiv(nblk, 256), 256, 0, st>>>(g, E, ntx, nty, work)));
         const int ctas = (int)std::min<long long>(nblk, (long long)sm_count() * 6);
@@ -350,7 +383,7 @@ int launch_bwd2(const Geo &g, T isoT, T ix, T iy, T iz, const uint4 *E, const T 
         // list of the touched blocks: private to this call (stream-ordered allocation), so backward passes that share one
         // saved state -- retained graphs, several streams -- never race on it
         unsigned *work = nullptr;
-        CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&work), ((size_t)nblk + 16) * sizeof(unsigned), st));
+        CU_TRY(call_scratch(reinterpret_cast<void **>(&work), ((size_t)nblk + 16) * sizeof(unsigned), st));
         CU_TRY(cudaMemsetAsync(work, 0, 64, st));
         LAUNCH("mc_backward_mark", st, (bwd_mark_kernel<BX, BY><<<cdiv(nblk, 256), 256, 0, st>>>(g, E, ntx, nty, work)));
         const int ctas = (int)std::min<long long>(nblk, (long long)sm_count() * 6);
