@@ -235,38 +235,46 @@ def _extract_slab_fused(alg, sdf_own, deform_own, a, b, X, isovalue, normalize, 
 
 
 class _HaloGrad(Function):
-    """Identity on an extended slab whose halo layers were refreshed in place; backward returns the halo layers'
-    gradients to their owners (two neighbour messages) and adds what the neighbours send for OUR boundary layers.
-    The incoming gradient is updated in place (it is the dense tensor our own backward just produced)."""
+    """Identity on extended slabs whose halo layers were refreshed in place (one or several tensors of the same rank
+    layout, e.g. sdf and deform); backward returns the halo layers' gradients to their owners and adds what the
+    neighbours send for OUR boundary layers -- ONE batch of neighbour messages for all tensors.  The incoming
+    gradients are updated in place (they are the dense tensors our own backward just produced)."""
 
     @staticmethod
-    def forward(ctx, ext, rank, world, group):
+    def forward(ctx, rank, world, group, *exts):
         ctx.rank, ctx.world, ctx.group = rank, world, group
-        return ext.view_as(ext)
+        out = tuple(e.view_as(e) for e in exts)
+        return out if len(out) > 1 else out[0]
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, *gs):
         rank, world, group = ctx.rank, ctx.world, ctx.group
         n_lo = HALO if rank > 0 else 0
         n_hi = HALO if rank < world - 1 else 0
-        if not g.is_contiguous():
-            g = g.contiguous()
-        n = g.shape[0]
-        from_prev = g.new_empty((HALO,) + g.shape[1:]) if n_lo else None
-        from_next = g.new_empty((HALO,) + g.shape[1:]) if n_hi else None
-        spec = []
-        if n_lo:        # my lo halo belongs to prev's last layers; prev's hi halo are my first layers
-            spec += [("send", g[:HALO], rank - 1), ("recv", from_prev, rank - 1)]
-        if n_hi:
-            spec += [("send", g[n - HALO:], rank + 1), ("recv", from_next, rank + 1)]
+        gs = [None if g is None else (g if g.is_contiguous() else g.contiguous()) for g in gs]
+        live = [g for g in gs if g is not None]
+        # a tensor whose gradient was not asked for on THIS rank still takes part in the exchange on the others:
+        # ranks must agree on the message list, so every rank differentiates the same set of fields (documented)
+        spec, recv = [], []
+        for g in live:
+            n = g.shape[0]
+            from_prev = g.new_empty((HALO,) + g.shape[1:]) if n_lo else None
+            from_next = g.new_empty((HALO,) + g.shape[1:]) if n_hi else None
+            if n_lo:        # my lo halo belongs to prev's last layers; prev's hi halo are my first layers
+                spec += [("send", g[:HALO], rank - 1), ("recv", from_prev, rank - 1)]
+            if n_hi:
+                spec += [("send", g[n - HALO:], rank + 1), ("recv", from_next, rank + 1)]
+            recv.append((from_prev, from_next))
         _p2p(spec, group)
-        if n_lo:
-            g[n_lo: n_lo + HALO] += from_prev
-            g[:n_lo] = 0
-        if n_hi:
-            g[n - n_hi - HALO: n - n_hi] += from_next
-            g[n - n_hi:] = 0
-        return g, None, None, None
+        for g, (from_prev, from_next) in zip(live, recv):
+            n = g.shape[0]
+            if n_lo:
+                g[n_lo: n_lo + HALO] += from_prev
+                g[:n_lo] = 0
+            if n_hi:
+                g[n - n_hi - HALO: n - n_hi] += from_next
+                g[n - n_hi:] = 0
+        return (None, None, None) + tuple(gs)
 
 
 class SlabField:
@@ -294,27 +302,51 @@ class SlabField:
         if self.world == 1:
             return
         with torch.no_grad():
-            e, n_lo, n = self.ext.detach(), self.n_lo, self.n
-            spec = []
-            if self.n_lo:
-                spec += [("send", e[n_lo: n_lo + HALO], self.rank - 1), ("recv", e[:n_lo], self.rank - 1)]
-            if self.n_hi:
-                spec += [("send", e[n_lo + n - HALO: n_lo + n], self.rank + 1), ("recv", e[n_lo + n:], self.rank + 1)]
-            _p2p(spec, self.group)
+            _p2p(self._refresh_spec(), self.group)
+
+    def _refresh_spec(self):
+        e, n_lo, n = self.ext.detach(), self.n_lo, self.n
+        spec = []
+        if self.n_lo:
+            spec += [("send", e[n_lo: n_lo + HALO], self.rank - 1), ("recv", e[:n_lo], self.rank - 1)]
+        if self.n_hi:
+            spec += [("send", e[n_lo + n - HALO: n_lo + n], self.rank + 1), ("recv", e[n_lo + n:], self.rank + 1)]
+        return spec
 
     def synced(self):
         """The extended tensor with fresh halos, wired into autograd (use this in the forward)."""
         self.refresh()
-        return _HaloGrad.apply(self.ext, self.rank, self.world, self.group) if self.world > 1 else self.ext
+        return _HaloGrad.apply(self.rank, self.world, self.group, self.ext) if self.world > 1 else self.ext
 
 
-def extract_slab_ext(alg, sdf_field, deform_field, x_range, X, isovalue=0.0, normalize=True, group=None, grad_mode="reference"):
+def sync_fields(fields, refresh=True):
+    """Several SlabFields of one rank layout (e.g. sdf and deform) at once: ONE batch of neighbour messages refreshes all
+    their halos, and one joint autograd node returns all their halo gradients in one batch during backward.
+    refresh=False: the halos are known to be current (a second extraction from unchanged fields in the same step)."""
+    fields = [f for f in fields if f is not None]
+    f0 = fields[0]
+    if f0.world == 1:
+        return [f.ext for f in fields]
+    if refresh:
+        with torch.no_grad():
+            spec = []
+            for f in fields:
+                spec += f._refresh_spec()
+            _p2p(spec, f0.group)
+    out = _HaloGrad.apply(f0.rank, f0.world, f0.group, *[f.ext for f in fields])
+    return list(out) if isinstance(out, tuple) else [out]
+
+
+def extract_slab_ext(alg, sdf_field, deform_field, x_range, X, isovalue=0.0, normalize=True, group=None, grad_mode="reference",
+                     refresh=True):
     """extract_slab for :class:`SlabField` inputs (the extended slab is the leaf: no per-step copy of the slab,
-    one host synchronisation per extraction).  Same return values as :func:`extract_slab`."""
+    one host synchronisation per extraction, one batch of halo messages per direction).  Same return values as
+    :func:`extract_slab`.  refresh=False skips the halo refresh (fields unchanged since the last refresh)."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     a, b = x_range
-    sdf_ext = sdf_field.synced()
-    def_ext = deform_field.synced() if deform_field is not None else None
+    exts = sync_fields([sdf_field, deform_field], refresh)
+    sdf_ext = exts[0]
+    def_ext = exts[1] if deform_field is not None else None
     return _extract_ext(alg, sdf_ext, def_ext, a, b, X, isovalue, normalize, group, rank, world, grad_mode)
 
 
