@@ -99,7 +99,7 @@ class _Base:
                 scratch = torch.empty((max(nf, 1), 3), dtype=self._dtype, device=grid.device)
                 _lib.check(L.diso_b200_dmc_backward(grid.data_ptr(), p(deform), dt, X, Y, Z, float(iso), state.data_ptr(),
                                                     ctypes.cast(counts_c, ctypes.c_void_p),
-                                                    adj_verts.data_ptr(), 0, None, _lib.GRAD_REFERENCE, None, 0, scratch.data_ptr(),
+                                                    adj_verts.data_ptr(), 0, None, _lib.GRAD_REFERENCE, None, 0, None, scratch.data_ptr(),
                                                     g_grid.data_ptr(), p(g_def), st))
             adj_grid.add_(g_grid)          # the reference accumulates into the caller's buffers (atomicAdd)
             if adj_deform is not None:

@@ -132,7 +132,7 @@ class _Extract(Function):
         # saved edge records (include/diso_b200.h: edge_rec): only when a gradient can be asked for later
         rec = None
         if ctx.needs_input_grad[0] or (deform is not None and ctx.needs_input_grad[1]):
-            rec = torch.empty((_blocks32(n_edges), 5, 32), dtype=grid.dtype, device=grid.device)
+            rec = torch.empty((_blocks32(n_edges), 5 if alg == _lib.ALG_MC else 6, 32), dtype=grid.dtype, device=grid.device)
         args = (grid.data_ptr(), _ptr(deform), _DTYPES[grid.dtype], X, Y, Z, float(isovalue), state.data_ptr(),
                 ctypes.cast(ctx.counts, ctypes.c_void_p), int(bool(normalize)), _lib.frame_ptr(ctx.frame))
         if alg == _lib.ALG_MC:
@@ -148,7 +148,12 @@ class _Extract(Function):
         ctx.n_edges = n_edges
         ctx.has_rec = rec is not None
         if rec is not None:
-            ctx.save_for_backward(grid, deform, state, rec)
+            # (DMC: the quads themselves are what the backward gathers dL/d dual-vertices with; they are saved as an
+            #  output, so modifying them in place before backward raises autograd's usual error)
+            if alg == _lib.ALG_MC:
+                ctx.save_for_backward(grid, deform, state, rec)
+            else:
+                ctx.save_for_backward(grid, deform, state, rec, faces)
         else:
             ctx.save_for_backward(grid, deform, state)
         ctx.mark_non_differentiable(faces)
@@ -158,10 +163,12 @@ class _Extract(Function):
 
     @staticmethod
     def backward(ctx, adj_verts, adj_faces):
-        if ctx.has_rec:
-            grid, deform, state, rec = ctx.saved_tensors
+        if ctx.has_rec and ctx.alg != _lib.ALG_MC:
+            grid, deform, state, rec, faces = ctx.saved_tensors
+        elif ctx.has_rec:
+            (grid, deform, state, rec), faces = ctx.saved_tensors, None
         else:
-            (grid, deform, state), rec = ctx.saved_tensors, None
+            (grid, deform, state), rec, faces = ctx.saved_tensors, None, None
         L = _lib.load()
         X, Y, Z = grid.shape
         need_grid = ctx.needs_input_grad[0]
@@ -193,7 +200,7 @@ class _Extract(Function):
                 _lib.check(L.diso_b200_dmc_backward(grid.data_ptr(), _ptr(deform), dt, X, Y, Z, ctx.isovalue,
                                                     state.data_ptr(), ctypes.cast(ctx.counts, ctypes.c_void_p),
                                                     adj_verts.data_ptr(), int(ctx.normalize), _lib.frame_ptr(ctx.frame),
-                                                    ctx.grad_mode, _ptr(rec), max(ctx.n_edges, 1), _ptr(scratch),
+                                                    ctx.grad_mode, _ptr(rec), max(ctx.n_edges, 1), _ptr(faces) if fused else None, _ptr(scratch),
                                                     _ptr(adj_grid), _ptr(adj_deform), _stream()))
         return (adj_grid if need_grid else None, adj_deform if need_deform else None) + rest
 

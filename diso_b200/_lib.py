@@ -44,7 +44,7 @@ SIGNATURES = {
     "diso_b200_mc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _vp]),
     "diso_b200_dmc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "diso_b200_mc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
-    "diso_b200_dmc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _i, _vp, _i, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "diso_b200_dmc_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _i, _vp, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "diso_b200_quad_split_scratch_bytes": (_sz, [_i64]),
     "diso_b200_quad_split": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp, _vp]),
     "diso_b200_debug_cell_codes": (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),

@@ -270,8 +270,8 @@ int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const 
     kernel_attrs(reinterpret_cast<const void *>(edge_verts_kernel<T, true>), "DISO_CARVEOUT_EV", -1);
     kernel_attrs(reinterpret_cast<const void *>(edge_verts_kernel<T, false>), "DISO_CARVEOUT_EV", -1);
     if (te.ctas) {
-        if (te.list) LAUNCH("mc_emit_verts", st, (edge_verts_kernel<T, true><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, te.n_active, verts, rec)));
-        else LAUNCH("mc_emit_verts", st, (edge_verts_kernel<T, false><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, te.n_active, verts, rec)));
+        if (te.list) LAUNCH("mc_emit_verts", st, (edge_verts_kernel<T, true><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, te.n_active, verts, rec, 5)));
+        else LAUNCH("mc_emit_verts", st, (edge_verts_kernel<T, false><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, te.n_active, verts, rec, 5)));
     }
     if (tc.ctas) {
         const uint2 *F = reinterpret_cast<const uint2 *>(p.aux);
@@ -298,15 +298,15 @@ int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const
     kernel_attrs(reinterpret_cast<const void *>(dmc_edges2_kernel<T, 0, true>), "DISO_CARVEOUT_QUAD", -1);
     kernel_attrs(reinterpret_cast<const void *>(dmc_edges2_kernel<T, 0, false>), "DISO_CARVEOUT_QUAD", -1);
     if (te.ctas) {
-        if (te.list) LAUNCH("dmc_edge_crossings", st, (edge_verts_kernel<T, true><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch, rec)));
-        else LAUNCH("dmc_edge_crossings", st, (edge_verts_kernel<T, false><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch, rec)));
+        if (te.list) LAUNCH("dmc_edge_crossings", st, (edge_verts_kernel<T, true><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch, rec, 6)));
+        else LAUNCH("dmc_edge_crossings", st, (edge_verts_kernel<T, false><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch, rec, 6)));
     }
     if (tc.ctas) {
         if (tc.list) LAUNCH("dmc_emit_verts", st, (dmc_dual_verts_kernel<T, true><<<tc.ctas, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, tc.list, tc.n_active, verts)));
         else LAUNCH("dmc_emit_verts", st, (dmc_dual_verts_kernel<T, false><<<tc.ctas, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, tc.list, tc.n_active, verts)));
     }
     if (te.ctas) {
-#define DISO_QUADS(LISTED, OFFSET, DIAG) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, LISTED, OFFSET, DIAG><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, fr.id_offset, quads, nullptr, 0, verts, qflags)))
+#define DISO_QUADS(LISTED, OFFSET, DIAG) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, LISTED, OFFSET, DIAG><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, fr.id_offset, quads, nullptr, 0, verts, qflags, rec)))
         if (qflags) {
             if (fr.id_offset != 0) { if (te.list) DISO_QUADS(true, true, true); else DISO_QUADS(false, true, true); }
             else                   { if (te.list) DISO_QUADS(true, false, true); else DISO_QUADS(false, false, true); }
@@ -405,7 +405,7 @@ int launch_bwd2(const Geo &g, T isoT, T ix, T iy, T iz, const uint4 *E, const T 
 template <typename T>
 int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const int64_t *counts_host,
                      const T *gsrc, int gsrc_kind, const T *rec, int normalize, int X_global, T *adj_sdf, T *adj_deform,
-                     cudaStream_t st)
+                     cudaStream_t st, const long long *quads = nullptr, long long id_offset = 0)
 {
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     // chain rule of verts / (dims - 1): multiply by the reciprocal (gradients carry a 1e-5 bar, not bit parity)
@@ -418,7 +418,7 @@ int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, co
     bool sparse = counts_host && counts_host[DISO_CNT_EDGE_CHUNKS] * 8 < (long long)g.NCH && g.NCH >= 65536;
     if (force >= 0) sparse = force != 0;
     if (rec) {
-        DmcSrc dmc{p.S, reinterpret_cast<const uint4 *>(p.aux), p.C};
+        DmcSrc dmc{quads, id_offset};
 #define DISO_B2(HD, K) launch_bwd2<T, HD, K, BWD2_BX, BWD2_BY>(g, isoT, ix, iy, iz, p.E, gsrc, dmc, rec, adj_sdf, HD ? adj_deform : nullptr, sparse, st)
         if (deform) {
             switch (gsrc_kind) { case 1: return DISO_B2(true, 1); case 2: return DISO_B2(true, 2); case 3: return DISO_B2(true, 3); default: return DISO_B2(true, 0); }
@@ -437,8 +437,8 @@ int mc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, co
 
 template <typename T>
 int dmc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, const StatePtrs &p, const int64_t *counts_host,
-                      const T *adj_verts, const T *rec, int normalize, int X_global, int grad_mode, T *scratch, T *adj_sdf,
-                      T *adj_deform, cudaStream_t st)
+                      const T *adj_verts, const T *rec, const long long *quads, long long id_offset, int normalize, int X_global, int grad_mode,
+                      T *scratch, T *adj_sdf, T *adj_deform, cudaStream_t st)
 {
     const uint4 *P = reinterpret_cast<const uint4 *>(p.aux);
     const T ix = normalize ? T(1) / (T(X_global) - T(1)) : T(1), iy = normalize ? T(1) / (T(g.Y) - T(1)) : T(1),
@@ -447,9 +447,9 @@ int dmc_backward_impl(const T *sdf, const T *deform, const Geo &g, double iso, c
         // saved records: ONE kernel, like the reference's adj_create_dmc_verts (cudualmc.cu:957-1005): the per-edge adjoint
         // is evaluated inside the edge pass of mc_backward2 (no per-edge array, one edge list instead of two)
         static const int unfused = env_int("DISO_DMC_BWD_UNFUSED", 0);   // experiment knob: stage A as its own kernel
-        if (!unfused)
+        if (!unfused && quads)
             return mc_backward_impl<T>(sdf, deform, g, iso, p, counts_host, adj_verts, grad_mode == DISO_GRAD_EXACT ? 2 : 3, rec, normalize,
-                                       X_global, adj_sdf, adj_deform, st);
+                                       X_global, adj_sdf, adj_deform, st, quads, id_offset);
         if (!scratch) return fail(DISO_E_INVALID, "scratch required");
     }
     const TileGrid te = tile_grid(p, g, counts_host, 0);
@@ -617,11 +617,11 @@ int diso_b200_mc_backward(const void *sdf, const void *deform, int dtype, int X,
 int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z, double iso,
                            void *state, const int64_t *counts_host, const void *adj_verts, int normalize,
                            const diso_b200_frame *frame, int grad_mode, const void *edge_rec, int64_t edge_rec_stride,
-                           void *scratch, void *adj_sdf, void *adj_deform, void *stream)
+                           const int64_t *quads, void *scratch, void *adj_sdf, void *adj_deform, void *stream)
 {
     int rc = check_dims(DISO_ALG_DMC, dtype, X, Y, Z);
     if (rc) return rc;
-    if (!sdf || !state || !adj_verts || (!scratch && !edge_rec)) return fail(DISO_E_INVALID, "null pointer");
+    if (!sdf || !state || !adj_verts || (!scratch && !(edge_rec && quads))) return fail(DISO_E_INVALID, "null pointer");
     if (!deform && adj_deform) return fail(DISO_E_INVALID, "adj_deform given without deform");
     if (!edge_rec && (!adj_sdf || (deform != nullptr) != (adj_deform != nullptr)))
         return fail(DISO_E_INVALID, "without edge_rec, adj_sdf is required and adj_deform must be given iff deform is");
@@ -635,10 +635,12 @@ int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X
     if (dtype == DISO_F32)
         return dmc_backward_impl<float>(static_cast<const float *>(sdf), static_cast<const float *>(deform), g, iso, p, counts_host,
                                         static_cast<const float *>(adj_verts), static_cast<const float *>(edge_rec),
+                                        reinterpret_cast<const long long *>(quads), fr.id_offset,
                                         normalize, fr.X_global, grad_mode, static_cast<float *>(scratch),
                                         static_cast<float *>(adj_sdf), static_cast<float *>(adj_deform), st);
     return dmc_backward_impl<double>(static_cast<const double *>(sdf), static_cast<const double *>(deform), g, iso, p, counts_host,
                                      static_cast<const double *>(adj_verts), static_cast<const double *>(edge_rec),
+                                     reinterpret_cast<const long long *>(quads), fr.id_offset,
                                      normalize, fr.X_global, grad_mode, static_cast<double *>(scratch),
                                      static_cast<double *>(adj_sdf), static_cast<double *>(adj_deform), st);
 }

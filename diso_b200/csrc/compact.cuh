@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(CT_THREADS) edge_verts_kernel(const T *__restr
                                                               Geo g, T iso, T padv, EpilogueC<T> epi,
                                                               const uint4 *__restrict__ E,
                                                               const unsigned *__restrict__ alist, int n_active,
-                                                              T *__restrict__ verts, T *__restrict__ rec)
+                                                              T *__restrict__ verts, T *__restrict__ rec, int rec_ncomp)
 {
     __shared__ unsigned short s_list[CT_MAX_EDGES];
     __shared__ TilePos s_pos[CT_CHUNKS];
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(CT_THREADS) edge_verts_kernel(const T *__restr
             // saved for the backward (mc_backward_v2.cuh): everything adjComputeMcVert (cumc.cu:412-453) needs of this
             // edge, as five arrays indexed by rank -- coalesced here and there, no sdf / deform gathers in the backward
             // (groups of 32 edges, component-major inside a group: mc_backward_v2.cuh:blk_index)
-            T *r = rec + (rank >> 5) * 160 + (rank & 31);
+            T *r = rec + (rank >> 5) * (size_t)(32 * rec_ncomp) + (rank & 31);   // rec_ncomp: 5 (MC) or 6 (DMC: + quad meta)
             r[0] = dp.x; r[32] = dp.y; r[64] = dp.z; r[96] = d0; r[128] = d1;
         }
     }

@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
                                                               const unsigned *__restrict__ alist, int n_active, T ix, T iy, T iz,
                                                               const T *__restrict__ adj_dual, long long id_offset,
                                                               long long *__restrict__ quads, T *__restrict__ gedge, int gedge_soa,
-                                                              const T *__restrict__ verts = nullptr, unsigned char *__restrict__ qflags = nullptr)
+                                                              const T *__restrict__ verts = nullptr, unsigned char *__restrict__ qflags = nullptr,
+                                                              T *__restrict__ rec = nullptr)
 {
     __shared__ unsigned short s_list[CT_MAX_EDGES];
     __shared__ unsigned s_case[256];
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
     __shared__ T s_inv[8];
     __shared__ int s_k[LISTED ? CT_CHUNKS : 1];
     s_case[threadIdx.x] = T_DMC_CASE[threadIdx.x];
-    if (MODE != 0) s_plen[threadIdx.x] = T_DMC_PATCHLEN[threadIdx.x];
+    s_plen[threadIdx.x] = T_DMC_PATCHLEN[threadIdx.x];
     if (threadIdx.x < 6) s_quad[threadIdx.x] = T_DMC_QUAD[threadIdx.x];
     if (threadIdx.x < 8) s_inv[threadIdx.x] = threadIdx.x ? T(1) / T((int)threadIdx.x) : T(0);
     const TileRange<LISTED> tr(alist, n_active);
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
         // shared memory measured slower)
         const unsigned q4 = s_quad[inside * 3 + axis];
         long long id[4];
+        unsigned meta = 0;   // MODE 0: per corner {patch length : 3, index of the patch inside its cell : 2}
         Vec3<T> acc{T(0), T(0), T(0)};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -70,6 +72,7 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
             const unsigned ord = (s_case[code] >> (2 * eid)) & 3u;
             if (MODE == 0) {
                 id[c] = (long long)(first + ord);
+                meta |= (((s_plen[code] >> (4 * ord)) & 7u) | (ord << 3)) << (5 * c);
             } else {
                 const unsigned src = (MODE == 1) ? first + ord : first;
                 const T inv = s_inv[(s_plen[code] >> (4 * ord)) & 7u];
@@ -81,6 +84,9 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
         }
         const size_t rank = (size_t)tile_base + i;
         if (MODE == 0) {
+            // saved for the backward (6th record component, mc_backward_v2.cuh): with the quad's four ids the adjoint of
+            // the dual-vertex averaging needs no cell / patch lookups at all
+            if (rec) reinterpret_cast<unsigned *>(rec + (rank >> 5) * 192 + 160 + (rank & 31))[0] = meta;
             if (DIAG) {   // local ids index the local vertex array (the slab offset is added below)
                 Vec3<T> v[4];
 #pragma unroll

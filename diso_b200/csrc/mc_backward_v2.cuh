@@ -71,10 +71,8 @@ template <typename T, bool HAS_DEF, bool DMC, int BX, int BY> struct Bwd2Layout 
     static constexpr size_t off_delta = off_zin + ROWS * 4;                // u32 [ROWS]       own rows: rank - list slot
     static constexpr size_t off_info = (off_delta + ROWS * 4 + 15) / 16 * 16;  // int4 [ROWS]  accumulator bases {own, +x target, +y target, -}
     static constexpr size_t off_rowb = off_info + ROWS * 16;               // i64 [ROWS]       output element of lane 0 (own rows)
-    static constexpr size_t off_rowk = off_rowb + ROWS * 8;                // i32 [ROWS]       chunk id of the row (DMC: cells around an edge)
-    static constexpr size_t off_sign = off_rowk + (DMC ? ROWS * 4 : 0);    // u32 [ROWS]       sign word of the row's chunk (DMC)
-    static constexpr size_t off_tab = (off_sign + (DMC ? ROWS * 4 : 0) + 15) / 16 * 16;    // DMC tables: case[256], plen[256], quad[8], inv[8]
-    static constexpr size_t off_stage = off_tab + (DMC ? 2 * 256 * 4 + 8 * 4 + 8 * sizeof(T) + 16 : 0);  // T [WARPS][96] (deform write-out)
+    static constexpr size_t off_tab = (off_rowb + ROWS * 8 + 15) / 16 * 16;    // DMC: 1 / patch length, T [8]
+    static constexpr size_t off_stage = off_tab + (DMC ? 8 * sizeof(T) : 0);   // T [WARPS][96] (deform write-out)
     static constexpr size_t off_list = (off_stage + (HAS_DEF ? B2_WARPS * 96 * sizeof(T) : 0) + 15) / 16 * 16;   // u16 [CAP]
     static constexpr size_t bytes = off_list + (size_t)CAP * 2 + 16;
     static_assert(ROWS <= 64 && 4 * ROWS <= B2_THREADS, "four threads per row build the list; row index fits the descriptor");
@@ -86,11 +84,12 @@ template <typename T, bool HAS_DEF, bool DMC, int BX, int BY> struct Bwd2Layout 
 //   GSRC == 2 / 3: DMC, evaluated HERE (exact / reference-compatible adjoint of the dual-vertex averaging,
 //                  adj_create_dmc_verts, cudualmc.cu:957-1005, which is one kernel in the reference too): the edge's
 //                  adjoint is the sum over the 4 cells around it of adj_dual[patch of the edge in that cell] / len(patch).
-//                  No per-edge array is written or read, and the edge list is built once instead of twice.
+//                  The four dual-vertex ids ARE the edge's quad (the forward's own output, saved by autograd for free) and
+//                  the patch lengths / patch indices were saved by the quad kernel as a 6th record component, so this needs
+//                  no cell words, patch bases or case tables: two 128-bit loads + one word per edge, all by rank.
 struct DmcSrc {
-    const unsigned *S;          // sign words
-    const uint4 *P;             // {first dual vertex of the chunk, used, lo, hi}
-    const unsigned short *C;    // per cell: case index | offset of the first dual vertex << 8
+    const long long *quads;     // [n_quads, 4] the forward's quads (ids shifted by id_offset in a slab frame)
+    long long id_offset;
 };
 
 template <typename T, bool HAS_DEF, int GSRC, int BX, int BY, bool OUTPUTS_ZEROED>
@@ -111,12 +110,7 @@ __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T 
     unsigned *s_delta = reinterpret_cast<unsigned *>(smem2_raw + L::off_delta);
     int4 *s_info = reinterpret_cast<int4 *>(smem2_raw + L::off_info);
     long long *s_rowb = reinterpret_cast<long long *>(smem2_raw + L::off_rowb);
-    int *s_rowk = reinterpret_cast<int *>(smem2_raw + L::off_rowk);
-    unsigned *s_sign = reinterpret_cast<unsigned *>(smem2_raw + L::off_sign);
-    unsigned *s_case = reinterpret_cast<unsigned *>(smem2_raw + L::off_tab);
-    unsigned *s_plen = s_case + 256;
-    unsigned *s_quad = s_plen + 256;
-    T *s_inv = reinterpret_cast<T *>(s_quad + 8);
+    T *s_inv = reinterpret_cast<T *>(smem2_raw + L::off_tab);
     T *s_stage = reinterpret_cast<T *>(smem2_raw + L::off_stage);
     unsigned short *s_list = reinterpret_cast<unsigned short *>(smem2_raw + L::off_list);
 
@@ -135,17 +129,14 @@ __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T 
             const int k = (xp * g.PY + yp) * g.NC + c;
             r4 = E[k];
             if (c > 0 && dxr >= 1 && dyr >= 1) zin = E[k - 1].w >> 31;
-            if (DMC) { s_rowk[tid] = k; s_sign[tid] = dmc.S[k]; }
         }
-        unsigned zsign = 0;   // DMC: is the start point of that arriving edge inside? (bit 31 of the previous chunk's sign word)
-        if (DMC && zin) zsign = dmc.S[(xp * g.PY + yp) * g.NC + c - 1] >> 31;
         unsigned cnt;
         if (dxr >= 1 && dyr >= 1) cnt = __popc(r4.y) + __popc(r4.z) + __popc(r4.w) + zin;   // own row: every edge
         else if (dxr == 0 && dyr == 0) cnt = 0;              // corner: touches nothing
         else if (dxr == 0) cnt = __popc(r4.y);               // -x halo row: its +x edges end in the block
         else cnt = __popc(r4.z);                             // -y halo row: its +y edges
         s_rec[tid] = r4;
-        s_zin[tid] = zin | (zsign << 1);
+        s_zin[tid] = zin;
         s_off[tid] = cnt;
         mine_any = cnt != 0u;
         // accumulator slots of lane 0 of: this row (own rows), the row its +x edges end in, the row its +y edges end in
@@ -175,12 +166,7 @@ __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T 
         }
         return;
     }
-    if (DMC) {   // case tables of the dual-vertex adjoint (read-only until the barrier below)
-        s_case[tid] = T_DMC_CASE[tid];
-        s_plen[tid] = T_DMC_PATCHLEN[tid];
-        if (tid < 6) s_quad[tid] = T_DMC_QUAD[tid];
-        if (tid < 8) s_inv[tid] = tid ? T(1) / T(tid) : T(0);
-    }
+    if (DMC && tid < 8) s_inv[tid] = tid ? T(1) / T(tid) : T(0);   // (read after the barrier below)
     if (wid == 0) {  // exclusive scan of the ROWS counts (<= two per lane)
         constexpr int PER = (ROWS + 31) / 32;
         unsigned v[PER], sum = 0;
@@ -256,26 +242,21 @@ __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T 
                 if (axis == 1) rank += bit(r4.y, j);
             }
             T gx, gy, gz;
+            constexpr int NREC = GSRC >= 1 ? 6 : 5;   // record components per edge (DMC extractions: + the quad meta word)
+            const T *rp = rec + blk_index<NREC>(rank);
             if constexpr (DMC) {
-                // stage A of adj_create_dmc_verts (cudualmc.cu:957-1005), same operations and order as dmc_edges2_kernel<1|2>
-                int kq = s_rowk[r], jq = j;
-                unsigned inside;
-                if (j >= 0) inside = (s_sign[r] >> j) & 1u;
-                else { kq -= 1; jq = 31; inside = (s_zin[r] >> 1) & 1u; }
-                const unsigned q4 = s_quad[inside * 3 + axis];
+                // stage A of adj_create_dmc_verts (cudualmc.cu:957-1005): same operations and order as dmc_edges2_kernel<1|2>
+                const longlong2 *qp = reinterpret_cast<const longlong2 *>(dmc.quads + (size_t)rank * 4);
+                const longlong2 qa = __ldg(qp), qb = __ldg(qp + 1);
+                const unsigned meta = __ldg(reinterpret_cast<const unsigned *>(rp + 160));
+                const long long id[4] = {qa.x, qa.y, qb.x, qb.y};
                 Vec3<T> acc{T(0), T(0), T(0)};
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
-                    const unsigned b = (q4 >> (8 * cc)) & 0xffu;
-                    int kk = kq - (int)(b & 1u) * g.sX - (int)((b >> 1) & 1u) * g.sY;
-                    int jj = jq - (int)((b >> 2) & 1u);
-                    if (jj < 0) { kk -= 1; jj = 31; }
-                    const unsigned info = dmc.C[(size_t)kk * 32 + jj];
-                    const unsigned first = dmc.P[kk].x + (info >> 8);
-                    const unsigned code = info & 0xffu;
-                    const unsigned ord = (s_case[code] >> (2 * (b >> 4))) & 3u;
-                    const unsigned src = (GSRC == 2) ? first + ord : first;   // reference mode: the cell's FIRST dual vertex (cudualmc.cu:975,990)
-                    const T inv = s_inv[(s_plen[code] >> (4 * ord)) & 7u];
+                    const unsigned mm = meta >> (5 * cc);
+                    // reference mode: the cell's FIRST dual vertex (cudualmc.cu:975,990) = this patch's id - its index in the cell
+                    const long long src = id[cc] - dmc.id_offset - (GSRC == 3 ? (long long)((mm >> 3) & 3u) : 0ll);
+                    const T inv = s_inv[mm & 7u];
                     const T *pa = gsrc + (size_t)src * 3;
                     acc.x = fma_rn(__ldg(pa), inv, acc.x);
                     acc.y = fma_rn(__ldg(pa + 1), inv, acc.y);
@@ -287,7 +268,6 @@ __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T 
                 else { const T *gp = gsrc + (size_t)rank * 3; gx = __ldg(gp); gy = __ldg(gp + 1); gz = __ldg(gp + 2); }
                 gx = gx * ix; gy = gy * iy; gz = gz * iz;
             }
-            const T *rp = rec + blk_index<5>(rank);
             const T dpx = __ldg(rp), dpy = __ldg(rp + 32), dpz = __ldg(rp + 64), d0 = __ldg(rp + 96), d1 = __ldg(rp + 128);
             // adjComputeMcVert (cumc.cu:412-453) with one reciprocal: (iso - d1) / (d1 - d0)^2 * adj_t etc.
             T adj_t = dpx * gx;

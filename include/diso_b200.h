@@ -109,8 +109,9 @@ int diso_b200_read_counts(const void *state, int64_t *counts_host, void *stream)
  * diso_b200_count (the active-chunk counts size the launches; sparse surfaces then cost time
  * proportional to the surface, not the volume).  NULL = visit every chunk.
  *
- * edge_rec (ABI v3, may be NULL): caller-owned, 5 * 32 * ceil(edge_rec_stride / 32) elements of dtype with
- * edge_rec_stride >= #crossing edges (groups of 32 edges, component-major inside a group).  When given, the edge pass also SAVES, per crossing edge and indexed by its rank (== its MC vertex id ==
+ * edge_rec (ABI v3, may be NULL): caller-owned, NCOMP * 32 * ceil(edge_rec_stride / 32) elements of dtype with
+ * edge_rec_stride >= #crossing edges (groups of 32 edges, component-major inside a group); NCOMP = 5 for
+ * diso_b200_mc_emit and 6 for diso_b200_dmc_emit (the 6th word per edge holds the quad's patch lengths).  When given, the edge pass also SAVES, per crossing edge and indexed by its rank (== its MC vertex id ==
  * its DMC quad id), what the adjoint of computeMcVert needs (adjComputeMcVert, cumc.cu:412-453): p1 - p0 (x, y, z),
  * d0, d1.  Passing the same buffer to *_backward selects the saved-record backward, which reads neither sdf nor
  * deform; the reference instead re-runs the whole forward inside backward
@@ -150,14 +151,16 @@ int diso_b200_mc_backward(const void *sdf, const void *deform, int dtype, int X,
                           int64_t edge_rec_stride, void *adj_sdf, void *adj_deform, void *stream);
 
 /* Backward, dual marching cubes (replaces adj_create_dmc_verts, cudualmc.cu:957-1005).
- * scratch: caller-owned per-edge adjoints, n_quads*3 elements of dtype; may be NULL when edge_rec is given (the
- * per-edge adjoint is then evaluated inside the one backward kernel and never materialised).
+ * scratch: caller-owned per-edge adjoints, n_quads*3 elements of dtype; may be NULL when edge_rec AND quads are given.
+ * quads (may be NULL): the [n_quads,4] int64 output of diso_b200_dmc_emit.  With edge_rec and quads the whole adjoint is
+ * ONE kernel: the four dual vertices around an edge are its quad, the patch lengths were saved next to the records, so
+ * neither cell words nor case tables are consulted and no per-edge adjoint is materialised.
  * edge_rec / edge_rec_stride: as for diso_b200_mc_backward. */
 int diso_b200_dmc_backward(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
                            double iso, void *state, const int64_t *counts_host,
                            const void *adj_verts, int normalize, const diso_b200_frame *frame,
-                           int grad_mode, const void *edge_rec, int64_t edge_rec_stride, void *scratch,
-                           void *adj_sdf, void *adj_deform, void *stream);
+                           int grad_mode, const void *edge_rec, int64_t edge_rec_stride,
+                           const int64_t *quads, void *scratch, void *adj_sdf, void *adj_deform, void *stream);
 
 /* Quad -> triangle split of diso/__init__.py:118-147 as two kernels (no PyTorch
  * temporaries).  verts [n_verts,3] dtype (API frame), quads [n_quads,4] int64, faces

@@ -56,7 +56,8 @@ def test_dense_and_listed_tiles_agree(alg, dtype):
             faces = torch.full((nf, k), -1, dtype=torch.int64, device=DEV)
             adj_s = torch.full_like(sdf, float("nan"))
             adj_d = torch.full_like(deform, float("nan"))
-            rec = torch.full(((ne + 31) // 32, 5, 32), float("nan"), dtype=dtype, device=DEV) if use_rec else None
+            ncomp = 5 if alg == "mc" else 6
+            rec = torch.full(((ne + 31) // 32, ncomp, 32), float("nan"), dtype=dtype, device=DEV) if use_rec else None
             rp = rec.data_ptr() if use_rec else None
             w = torch.cos(torch.arange(nv * 3, dtype=torch.float64).reshape(nv, 3) * 0.618).to(dtype).to(DEV)
             common = (sdf.data_ptr(), deform.data_ptr(), dt, n, n, n, 0.0, state.data_ptr())
@@ -69,11 +70,11 @@ def test_dense_and_listed_tiles_agree(alg, dtype):
                 scratch = torch.empty(((ne + 31) // 32 * 32, 3), dtype=dtype, device=DEV)
                 _lib.check(L.diso_b200_dmc_emit(*common, ch, 1, None, scratch.data_ptr(), verts.data_ptr(), faces.data_ptr(), rp, ne, None, st))
                 for gm in (_lib.GRAD_REFERENCE, _lib.GRAD_EXACT):
-                    _lib.check(L.diso_b200_dmc_backward(*common, ch, w.data_ptr(), 1, None, gm, rp, ne, scratch.data_ptr(), adj_s.data_ptr(), adj_d.data_ptr(), st))
+                    _lib.check(L.diso_b200_dmc_backward(*common, ch, w.data_ptr(), 1, None, gm, rp, ne, faces.data_ptr() if use_rec else None, scratch.data_ptr(), adj_s.data_ptr(), adj_d.data_ptr(), st))
                     grads += [adj_s.clone(), adj_d.clone()]
             torch.cuda.synchronize()
             if use_rec:
-                flat = rec.permute(1, 0, 2).reshape(5, -1)[:, :ne]
+                flat = rec.permute(1, 0, 2).reshape(ncomp, -1)[:5, :ne]
                 assert bool(torch.isfinite(flat).all()), "edge records not fully written"
             res.append([t.cpu().numpy() for t in [verts, faces] + grads])
         for a, b, what in zip(res[0], res[1], ("verts", "faces", "adj_sdf", "adj_deform", "adj_sdf(exact)", "adj_deform(exact)")):
