@@ -299,8 +299,10 @@ __global__ void __launch_bounds__(SCAN_TILE, DISO_CLASSIFY_MINB)   // 32 registe
 #pragma unroll
     for (int i = 0; i < CW_STRIDE; ++i) s_cw[i * SCAN_TILE + tid] = 0u;
     if (tid == 0) s_any_cells = 0u;
-    if (ALG == DISO_ALG_MC) s_tab[tid] = (unsigned)(T_MC_CASE[tid] >> 60);
-    else                    s_tab[tid] = T_DMC_CASE[tid];
+    for (int i = tid; i < 256; i += SCAN_TILE) {
+        if (ALG == DISO_ALG_MC) s_tab[i] = (unsigned)(T_MC_CASE[i] >> 60);
+        else                    s_tab[i] = T_DMC_CASE[i];
+    }
     if (tid == 0) { s_tile = atomicAdd(ticket, 1u); s_used_tot = 0; }
     __syncthreads();
     const int tile = (int)s_tile;

@@ -65,7 +65,10 @@ struct __align__(64) TileDesc {
     unsigned long long incl[4];
 };
 
-constexpr int SCAN_TILE = 256;  // chunks per scan tile == threads per classify CTA
+#ifndef DISO_SCAN_TILE
+#define DISO_SCAN_TILE 256
+#endif
+constexpr int SCAN_TILE = DISO_SCAN_TILE;  // chunks per scan tile == threads per classify CTA
 #ifndef DISO_BWD_BX
 #define DISO_BWD_BX 4
 #define DISO_BWD_BY 6
