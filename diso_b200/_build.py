@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdiso_b200.so")
 SOURCES = ["api.cu"]
-DEPS = ["api.cu", "common.cuh", "classify.cuh", "edge_math.cuh", "mc_backward_compact.cuh", "compact.cuh", "dmc_compact.cuh", "quad_split.cuh",
+DEPS = ["api.cu", "common.cuh", "classify.cuh", "edge_math.cuh", "mc_backward_compact.cuh", "mc_backward_v2.cuh", "compact.cuh", "dmc_compact.cuh", "quad_split.cuh",
         "tables.cuh", "case_tables.inc", os.path.join("..", "..", "include", "diso_b200.h")]
 
 NVCC_FLAGS = [
