@@ -176,6 +176,9 @@ def kernel_bytes(name, G, s, c_mc, c_dmc, deform):
         "classify_scan_mc": 0, "classify_scan_dmc": 0,
         "mc_emit_verts": 3 * Vm * s + d3 * min(Em, G) * s,
         "mc_emit_tris": 3 * Fm * 8,
+        # one launch: edge pass + triangle pass (CTAs interleaved) / edge crossings + quads
+        "mc_emit_fused": 3 * Vm * s + d3 * min(Em, G) * s + 3 * Fm * 8,
+        "dmc_emit_cross_quads": d3 * min(Em, G) * s + 4 * Qd * 8,
         "mc_backward": 3 * Vm * s + min(Em, G) * s + G * s + d3 * (min(Em, G) + G) * s,
         "dmc_edge_crossings": d3 * min(Em, G) * s,   # internal pass: reads the deform endpoints
         "dmc_emit_verts": 3 * Vd * s,

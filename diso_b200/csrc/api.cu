@@ -267,6 +267,17 @@ int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const 
     const T isoT = (T)iso, padv = (T)(iso + 1.0);
     const EpilogueC<T> epi = make_epilogue_c<T>(g, fr, normalize);
     const TileGrid te = tile_grid(p, g, counts_host, 0), tc = tile_grid(p, g, counts_host, 1);
+    // Experiment (opt-in, DISO_EMIT_FUSION=1): ONE launch with edge-pass and triangle-pass CTAs interleaved, so that the
+    // DRAM-bound pass and the LSU-bound pass share every SM (compact.cuh: mc_emit_fused_kernel).  Measured at 512^3: 2.01 ms
+    // against 0.82 + 0.90 ms back to back -- the union of the two shared-memory footprints (28.8 KB x 7 CTAs) leaves ~20 KB of L1
+    // and the edge pass's sdf / deform gathers live on L1 capacity.  Off by default.
+    static const int fuse = env_int("DISO_EMIT_FUSION", 0);
+    if (fuse && te.ctas && tc.ctas && !te.list && !tc.list && te.ctas == tc.ctas) {
+        const uint2 *F = reinterpret_cast<const uint2 *>(p.aux);
+        if (fr.id_offset != 0) LAUNCH("mc_emit_fused", st, (mc_emit_fused_kernel<T, true><<<2 * te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, F, p.C, fr.id_offset, verts, rec, tris)));
+        else LAUNCH("mc_emit_fused", st, (mc_emit_fused_kernel<T, false><<<2 * te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, F, p.C, fr.id_offset, verts, rec, tris)));
+        return DISO_OK;
+    }
     kernel_attrs(reinterpret_cast<const void *>(edge_verts_kernel<T, true>), "DISO_CARVEOUT_EV", -1);
     kernel_attrs(reinterpret_cast<const void *>(edge_verts_kernel<T, false>), "DISO_CARVEOUT_EV", -1);
     if (te.ctas) {
@@ -297,7 +308,14 @@ int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const
     kernel_attrs(reinterpret_cast<const void *>(dmc_dual_verts_kernel<T, false>), "DISO_CARVEOUT_DUAL", -1);
     kernel_attrs(reinterpret_cast<const void *>(dmc_edges2_kernel<T, 0, true>), "DISO_CARVEOUT_QUAD", -1);
     kernel_attrs(reinterpret_cast<const void *>(dmc_edges2_kernel<T, 0, false>), "DISO_CARVEOUT_QUAD", -1);
-    if (te.ctas) {
+    // Experiment (opt-in, DISO_EMIT_FUSION=1): crossings + quads in one launch (dmc_emit_fused_kernel): 1.55 ms against
+    // 0.83 + 0.77 ms -- within noise of the two launches, so the separate kernels (and their per-kernel accounting) stay.
+    static const int fuse = env_int("DISO_EMIT_FUSION", 0);
+    const bool fuse_cq = fuse && !qflags && te.ctas && !te.list;     // dense flavour, quads requested as quads
+    if (fuse_cq) {
+        if (fr.id_offset != 0) LAUNCH("dmc_emit_cross_quads", st, (dmc_emit_fused_kernel<T, true><<<2 * te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.S, p.E, P, p.C, fr.id_offset, scratch, rec, quads)));
+        else LAUNCH("dmc_emit_cross_quads", st, (dmc_emit_fused_kernel<T, false><<<2 * te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.S, p.E, P, p.C, fr.id_offset, scratch, rec, quads)));
+    } else if (te.ctas) {
         if (te.list) LAUNCH("dmc_edge_crossings", st, (edge_verts_kernel<T, true><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch, rec, 6)));
         else LAUNCH("dmc_edge_crossings", st, (edge_verts_kernel<T, false><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch, rec, 6)));
     }
@@ -305,7 +323,7 @@ int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const
         if (tc.list) LAUNCH("dmc_emit_verts", st, (dmc_dual_verts_kernel<T, true><<<tc.ctas, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, tc.list, tc.n_active, verts)));
         else LAUNCH("dmc_emit_verts", st, (dmc_dual_verts_kernel<T, false><<<tc.ctas, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, tc.list, tc.n_active, verts)));
     }
-    if (te.ctas) {
+    if (te.ctas && !fuse_cq) {
 #define DISO_QUADS(LISTED, OFFSET, DIAG) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, LISTED, OFFSET, DIAG><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, fr.id_offset, quads, nullptr, 0, verts, qflags, rec)))
         if (qflags) {
             if (fr.id_offset != 0) { if (te.list) DISO_QUADS(true, true, true); else DISO_QUADS(false, true, true); }

@@ -33,9 +33,9 @@ static_assert(CT_THREADS == 4 * CT_CHUNKS, "phase A maps four threads (one byte 
 template <bool LISTED> struct TileRange {
     int e0, count, kfirst, klast;
     const unsigned *alist;
-    __device__ __forceinline__ TileRange(const unsigned *__restrict__ al, int n_active) : alist(al)
+    __device__ __forceinline__ TileRange(const unsigned *__restrict__ al, int n_active, int tile) : alist(al)
     {
-        e0 = blockIdx.x * CT_CHUNKS;
+        e0 = tile * CT_CHUNKS;
         count = min(CT_CHUNKS, n_active - e0);
         kfirst = LISTED ? (int)__ldg(al + e0) : e0;
         klast = LISTED ? (int)__ldg(al + e0 + count - 1) : e0 + count - 1;
@@ -146,16 +146,23 @@ template <typename T> struct EpilogueC {
 // epi.normalize == 0 it produces the raw padded-frame crossings that the DMC dual-vertex
 // kernel averages (computeMcVert of cudualmc.cu:683-708, each edge evaluated once, not 4x).
 // ------------------------------------------------------------------------------------------
+// The tile bodies are device functions over an explicit shared-memory struct so that two of them can share one launch
+// (mc_emit_fused_kernel / dmc_emit_fused_kernel below: CTAs of a DRAM-bound and of an LSU-bound pass co-resident on every SM).
+struct EvSmem {
+    unsigned short list[CT_MAX_EDGES];
+    TilePos pos[CT_CHUNKS];
+};
+
 template <typename T, bool LISTED>
-__global__ void __launch_bounds__(CT_THREADS) edge_verts_kernel(const T *__restrict__ sdf, const T *__restrict__ deform,
-                                                              Geo g, T iso, T padv, EpilogueC<T> epi,
-                                                              const uint4 *__restrict__ E,
-                                                              const unsigned *__restrict__ alist, int n_active,
-                                                              T *__restrict__ verts, T *__restrict__ rec, int rec_ncomp)
+__device__ __forceinline__ void edge_verts_tile(EvSmem &sm, int tile, const T *__restrict__ sdf, const T *__restrict__ deform,
+                                                const Geo &g, T iso, T padv, const EpilogueC<T> &epi,
+                                                const uint4 *__restrict__ E,
+                                                const unsigned *__restrict__ alist, int n_active,
+                                                T *__restrict__ verts, T *__restrict__ rec, int rec_ncomp)
 {
-    __shared__ unsigned short s_list[CT_MAX_EDGES];
-    __shared__ TilePos s_pos[CT_CHUNKS];
-    const TileRange<LISTED> tr(alist, n_active);
+    unsigned short *s_list = sm.list;
+    TilePos *s_pos = sm.pos;
+    const TileRange<LISTED> tr(alist, n_active, tile);
     unsigned tile_base;
     const unsigned n = build_edge_list<LISTED, false>(g, E, tr, nullptr, s_list, s_pos, nullptr, tile_base);
     if (n == 0) return;
@@ -207,6 +214,17 @@ __global__ void __launch_bounds__(CT_THREADS) edge_verts_kernel(const T *__restr
             r[0] = dp.x; r[32] = dp.y; r[64] = dp.z; r[96] = d0; r[128] = d1;
         }
     }
+}
+
+template <typename T, bool LISTED>
+__global__ void __launch_bounds__(CT_THREADS) edge_verts_kernel(const T *__restrict__ sdf, const T *__restrict__ deform,
+                                                              Geo g, T iso, T padv, EpilogueC<T> epi,
+                                                              const uint4 *__restrict__ E,
+                                                              const unsigned *__restrict__ alist, int n_active,
+                                                              T *__restrict__ verts, T *__restrict__ rec, int rec_ncomp)
+{
+    __shared__ EvSmem sm;
+    edge_verts_tile<T, LISTED>(sm, blockIdx.x, sdf, deform, g, iso, padv, epi, E, alist, n_active, verts, rec, rec_ncomp);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -271,18 +289,26 @@ constexpr int CT_MAX_TRIS = CT_CHUNKS * 160;
 
 // OFFSET: add id_offset to every index (slab -> global ids); a separate instantiation keeps the 64-bit adds
 // out of the standalone kernel (they cost 2.5 % there).
+template <bool LISTED> struct TriSmem {
+    unsigned long long cases[256];
+    uint4 recs[CT_RECS];
+    unsigned short list[CT_MAX_TRIS];
+    __align__(8) unsigned char code[CT_CHUNKS * 32];
+    int k[LISTED ? CT_CHUNKS : 1];
+};
+
 template <bool LISTED, bool OFFSET>
-__global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const uint4 *__restrict__ E, const uint2 *__restrict__ F,
-                                                           const unsigned short *__restrict__ C,
-                                                           const unsigned *__restrict__ alist, int n_active,
-                                                           long long id_offset, long long *__restrict__ tris)
+__device__ __forceinline__ void mc_tris_tile(TriSmem<LISTED> &sm, int tile, const Geo &g, const uint4 *__restrict__ E,
+                                             const uint2 *__restrict__ F, const unsigned short *__restrict__ C,
+                                             const unsigned *__restrict__ alist, int n_active,
+                                             long long id_offset, long long *__restrict__ tris)
 {
-    __shared__ unsigned long long s_case[256];
-    __shared__ uint4 s_E[CT_RECS];
-    __shared__ unsigned short s_list[CT_MAX_TRIS];
-    __shared__ __align__(8) unsigned char s_code[CT_CHUNKS * 32];
-    __shared__ int s_k[LISTED ? CT_CHUNKS : 1];
-    const TileRange<LISTED> tr(alist, n_active);
+    unsigned long long *s_case = sm.cases;
+    uint4 *s_E = sm.recs;
+    unsigned short *s_list = sm.list;
+    unsigned char *s_code = sm.code;
+    int *s_k = sm.k;
+    const TileRange<LISTED> tr(alist, n_active, tile);
     const unsigned tile_base = F[tr.kfirst].x;
     const unsigned n = F[tr.klast + 1].x - tile_base;
     if (n == 0) return;
@@ -337,6 +363,36 @@ __global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const uint4 
         long long *dst = tris + (size_t)(tile_base + i) * 3;
         st_stream(dst, a); st_stream(dst + 1, b); st_stream(dst + 2, c);
     }
+}
+
+template <bool LISTED, bool OFFSET>
+__global__ void __launch_bounds__(CT_THREADS) mc_tris_kernel(Geo g, const uint4 *__restrict__ E, const uint2 *__restrict__ F,
+                                                           const unsigned short *__restrict__ C,
+                                                           const unsigned *__restrict__ alist, int n_active,
+                                                           long long id_offset, long long *__restrict__ tris)
+{
+    __shared__ TriSmem<LISTED> sm;
+    mc_tris_tile<LISTED, OFFSET>(sm, blockIdx.x, g, E, F, C, alist, n_active, id_offset, tris);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 + K4 in one launch (dense tile flavour): even CTAs run the edge pass of tile b/2, odd CTAs the triangle pass of the
+// same tile.  The edge pass is DRAM-bound (4.5 GB per launch with the saved records), the triangle pass is bound by
+// LSU wavefronts / issue slots with DRAM at 37 %: launched back to back each leaves the other's resource idle; co-resident
+// on every SM they overlap (0.82 + 0.90 -> see profiles/r2_backward.md).  The two passes share no data and no barrier.
+// ------------------------------------------------------------------------------------------
+template <typename T, bool OFFSET>
+__global__ void __launch_bounds__(CT_THREADS) mc_emit_fused_kernel(const T *__restrict__ sdf, const T *__restrict__ deform,
+                                                                 Geo g, T iso, T padv, EpilogueC<T> epi,
+                                                                 const uint4 *__restrict__ E, const uint2 *__restrict__ F,
+                                                                 const unsigned short *__restrict__ C, long long id_offset,
+                                                                 T *__restrict__ verts, T *__restrict__ rec,
+                                                                 long long *__restrict__ tris)
+{
+    __shared__ union U { EvSmem ev; TriSmem<false> tri; __device__ U() {} } sm;
+    const int tile = blockIdx.x >> 1;
+    if (blockIdx.x & 1) mc_tris_tile<false, OFFSET>(sm.tri, tile, g, E, F, C, nullptr, g.NCH, id_offset, tris);
+    else edge_verts_tile<T, false>(sm.ev, tile, sdf, deform, g, iso, padv, epi, E, nullptr, g.NCH, verts, rec, 5);
 }
 
 }  // namespace diso

@@ -22,27 +22,34 @@ namespace diso {
 // four dual-vertex ids are in registers: gathers the four (final, API-frame) vertices written by dmc_dual_verts and
 // stores one flag byte per quad; DiffDMC's default path then needs only a scan over those bytes (quad_diag<PRECOMPUTED>)
 // instead of re-reading the 32-byte quads and chasing ids -> vertices (2.15 ms at 512^3, latency-bound).
+template <typename T, bool LISTED> struct QuadSmem {
+    unsigned short list[CT_MAX_EDGES];
+    unsigned cases[256];
+    unsigned plen[256];
+    unsigned quad[8];
+    T inv[8];
+    int k[LISTED ? CT_CHUNKS : 1];
+};
+
 template <typename T, int MODE, bool LISTED, bool OFFSET = false, bool DIAG = false>
-__global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const unsigned *__restrict__ S,
-                                                              const uint4 *__restrict__ E, const uint4 *__restrict__ P,
-                                                              const unsigned short *__restrict__ C,
-                                                              const unsigned *__restrict__ alist, int n_active, T ix, T iy, T iz,
-                                                              const T *__restrict__ adj_dual, long long id_offset,
-                                                              long long *__restrict__ quads, T *__restrict__ gedge, int gedge_soa,
-                                                              const T *__restrict__ verts = nullptr, unsigned char *__restrict__ qflags = nullptr,
-                                                              T *__restrict__ rec = nullptr)
+__device__ __forceinline__ void dmc_edges2_tile(QuadSmem<T, LISTED> &sm, int tile, const Geo &g, const unsigned *__restrict__ S,
+                                                const uint4 *__restrict__ E, const uint4 *__restrict__ P,
+                                                const unsigned short *__restrict__ C,
+                                                const unsigned *__restrict__ alist, int n_active, T ix, T iy, T iz,
+                                                const T *__restrict__ adj_dual, long long id_offset,
+                                                long long *__restrict__ quads, T *__restrict__ gedge, int gedge_soa,
+                                                const T *__restrict__ verts, unsigned char *__restrict__ qflags,
+                                                T *__restrict__ rec)
 {
-    __shared__ unsigned short s_list[CT_MAX_EDGES];
-    __shared__ unsigned s_case[256];
-    __shared__ unsigned s_plen[256];
-    __shared__ unsigned s_quad[8];
-    __shared__ T s_inv[8];
-    __shared__ int s_k[LISTED ? CT_CHUNKS : 1];
+    unsigned short *s_list = sm.list;
+    unsigned *s_case = sm.cases, *s_plen = sm.plen, *s_quad = sm.quad;
+    T *s_inv = sm.inv;
+    int *s_k = sm.k;
     s_case[threadIdx.x] = T_DMC_CASE[threadIdx.x];
     s_plen[threadIdx.x] = T_DMC_PATCHLEN[threadIdx.x];
     if (threadIdx.x < 6) s_quad[threadIdx.x] = T_DMC_QUAD[threadIdx.x];
     if (threadIdx.x < 8) s_inv[threadIdx.x] = threadIdx.x ? T(1) / T((int)threadIdx.x) : T(0);
-    const TileRange<LISTED> tr(alist, n_active);
+    const TileRange<LISTED> tr(alist, n_active, tile);
     unsigned tile_base;
     const unsigned n = build_edge_list<LISTED, true>(g, E, tr, S, s_list, nullptr, s_k, tile_base);
     if (n == 0) return;
@@ -112,6 +119,40 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const uns
     }
 }
 
+template <typename T, int MODE, bool LISTED, bool OFFSET = false, bool DIAG = false>
+__global__ void __launch_bounds__(CT_THREADS) dmc_edges2_kernel(Geo g, const unsigned *__restrict__ S,
+                                                              const uint4 *__restrict__ E, const uint4 *__restrict__ P,
+                                                              const unsigned short *__restrict__ C,
+                                                              const unsigned *__restrict__ alist, int n_active, T ix, T iy, T iz,
+                                                              const T *__restrict__ adj_dual, long long id_offset,
+                                                              long long *__restrict__ quads, T *__restrict__ gedge, int gedge_soa,
+                                                              const T *__restrict__ verts = nullptr, unsigned char *__restrict__ qflags = nullptr,
+                                                              T *__restrict__ rec = nullptr)
+{
+    __shared__ QuadSmem<T, LISTED> sm;
+    dmc_edges2_tile<T, MODE, LISTED, OFFSET, DIAG>(sm, blockIdx.x, g, S, E, P, C, alist, n_active, ix, iy, iz, adj_dual, id_offset, quads, gedge,
+                                                   gedge_soa, verts, qflags, rec);
+}
+
+// Edge crossings + quads in one launch (dense tile flavour, return_quads path): even CTAs evaluate the crossings of tile b/2
+// (DRAM-bound: 4.5 GB per launch), odd CTAs emit the quads of the same tile (LSU-bound); see mc_emit_fused_kernel.
+template <typename T, bool OFFSET>
+__global__ void __launch_bounds__(CT_THREADS) dmc_emit_fused_kernel(const T *__restrict__ sdf, const T *__restrict__ deform,
+                                                                  Geo g, T iso, T padv, EpilogueC<T> raw, const unsigned *__restrict__ S,
+                                                                  const uint4 *__restrict__ E, const uint4 *__restrict__ P,
+                                                                  const unsigned short *__restrict__ C, long long id_offset,
+                                                                  T *__restrict__ scratch, T *__restrict__ rec,
+                                                                  long long *__restrict__ quads)
+{
+    __shared__ union U { EvSmem ev; QuadSmem<T, false> quad; __device__ U() {} } sm;
+    const int tile = blockIdx.x >> 1;
+    if (blockIdx.x & 1)
+        dmc_edges2_tile<T, 0, false, OFFSET, false>(sm.quad, tile, g, S, E, P, C, nullptr, g.NCH, T(1), T(1), T(1), nullptr, id_offset, quads, nullptr, 0,
+                                                   nullptr, nullptr, rec);
+    else
+        edge_verts_tile<T, false>(sm.ev, tile, sdf, deform, g, iso, padv, raw, E, nullptr, g.NCH, scratch, rec, 6);
+}
+
 }  // namespace diso
 
 namespace diso {
@@ -148,7 +189,7 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_dual_verts_kernel(const T *__r
     __shared__ uint4 s_E[CT_RECS];
     __shared__ T s_inv[8];
     __shared__ int s_k[LISTED ? CT_CHUNKS : 1];
-    const TileRange<LISTED> tr(alist, n_active);
+    const TileRange<LISTED> tr(alist, n_active, blockIdx.x);
     const unsigned tile_base = P[tr.kfirst].x;
     const unsigned n = P[tr.klast + 1].x - tile_base;
     if (n == 0) return;
