@@ -286,6 +286,7 @@ int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const 
     }
     if (tc.ctas) {
         const uint2 *F = reinterpret_cast<const uint2 *>(p.aux);
+        kernel_attrs(reinterpret_cast<const void *>(mc_tris_kernel<false, false>), "DISO_CARVEOUT_TRIS", -1);
 #define DISO_TRIS(LISTED, OFFSET) LAUNCH("mc_emit_tris", st, (mc_tris_kernel<LISTED, OFFSET><<<tc.ctas, CT_THREADS, 0, st>>>(g, p.E, F, p.C, tc.list, tc.n_active, fr.id_offset, tris)))
         if (fr.id_offset != 0) { if (tc.list) DISO_TRIS(true, true); else DISO_TRIS(false, true); }
         else                   { if (tc.list) DISO_TRIS(true, false); else DISO_TRIS(false, false); }
