@@ -383,12 +383,12 @@ int launch_bwd2(const Geo &g, T isoT, T ix, T iy, T iz, const uint4 *E, const T 
                 T *adj_sdf, T *adj_deform, bool sparse, cudaStream_t st)
 {
     const char *name = GSRC >= 2 ? "dmc_backward" : "mc_backward";
-    // Shared-memory carve-out: the edge pass keeps 8 (MC) / 20 (DMC, fused dual-vertex adjoint) loads per thread in flight and
+    // Shared-memory carve-out: the edge pass keeps 8 (MC) / 15 (DMC, with the dual-vertex adjoint) loads per thread in flight and
     // every pending line occupies L1, so L1 capacity bounds the memory-level parallelism: with the driver's default (all 228 KB
-    // shared for 8 CTAs/SM, 28 KB L1) the fp32 kernels take 1.92 / 3.53 ms at 512^3, with ~164 KB shared (6 CTAs, 92 KB L1) 1.54 /
-    // 2.63, with 132 KB 1.60 / 2.54 (sweep in profiles/r2_backward.md)
+    // shared for 8 CTAs/SM, 28 KB L1) the fp32 MC kernel takes 1.88 ms at 512^3, with 132 KB shared (6 CTAs of 20.6 KB, 96 KB L1)
+    // 1.44 ms; DMC: 100-116 KB shared 2.25 ms, 132 KB 2.28, 164 KB 2.43 (sweeps in profiles/r2_backward.md)
     const char *carve_env = GSRC >= 2 ? "DISO_CARVEOUT_DBWD" : "DISO_CARVEOUT_BWD2";
-    const int carve = GSRC >= 2 ? 58 : 72;
+    const int carve = GSRC >= 2 ? 50 : (sizeof(T) == 4 ? 58 : 72);   // fp64 MC: 72 % 2.88 ms, 58 % 2.97 ms
     using L = Bwd2Layout<T, HAS_DEF, (GSRC >= 2), BX, BY>;
     const size_t smem = L::bytes;
     const int ntx = cdiv(g.X, BX), nty = cdiv(g.Y, BY);

@@ -72,9 +72,12 @@ template <typename T, bool HAS_DEF, bool DMC, int BX, int BY> struct Bwd2Layout 
     static constexpr size_t off_info = (off_delta + ROWS * 4 + 15) / 16 * 16;  // int4 [ROWS]  accumulator bases {own, +x target, +y target, -}
     static constexpr size_t off_rowb = off_info + ROWS * 16;               // i64 [ROWS]       output element of lane 0 (own rows)
     static constexpr size_t off_tab = (off_rowb + ROWS * 8 + 15) / 16 * 16;    // DMC: 1 / patch length, T [8]
-    static constexpr size_t off_stage = off_tab + (DMC ? 8 * sizeof(T) : 0);   // T [WARPS][96] (deform write-out)
-    static constexpr size_t off_list = (off_stage + (HAS_DEF ? B2_WARPS * 96 * sizeof(T) : 0) + 15) / 16 * 16;   // u16 [CAP]
-    static constexpr size_t bytes = off_list + (size_t)CAP * 2 + 16;
+    // the edge list is dead once the last entry has been evaluated, the deform write-out stage (T [WARPS][96]) lives after that:
+    // they share one region (3 KB less per CTA: 7 instead of 6 CTAs fit the 164 KB carve-out)
+    static constexpr size_t off_list = (off_tab + (DMC ? 8 * sizeof(T) : 0) + 15) / 16 * 16;   // u16 [CAP]
+    static constexpr size_t off_stage = off_list;
+    static constexpr size_t stage_bytes = HAS_DEF ? B2_WARPS * 96 * sizeof(T) : 0;
+    static constexpr size_t bytes = off_list + ((size_t)CAP * 2 > stage_bytes ? (size_t)CAP * 2 : stage_bytes) + 16;
     static_assert(ROWS <= 64 && 4 * ROWS <= B2_THREADS, "four threads per row build the list; row index fits the descriptor");
 };
 
