@@ -175,8 +175,9 @@ constexpr int CT_MAX_PATCHES = CT_CHUNKS * 128;
 //            consecutive output ranks.  Same values in the same order => bit-identical.
 // ------------------------------------------------------------------------------------------
 template <typename T, bool LISTED>
-// fp32: 32 registers for 8 CTAs/SM (34 registers / 7 CTAs by default: 1.18 -> 1.11 ms at 512^3, no spills)
-__global__ void __launch_bounds__(CT_THREADS, sizeof(T) == 4 ? 8 : 1) dmc_dual_verts_kernel(const T *__restrict__ mcv, Geo g, EpilogueC<T> epi,
+// fp32: 32 registers for 8 CTAs/SM (34 registers / 7 CTAs by default: 1.18 -> 1.11 ms at 512^3, no spills); fp64: 64 registers
+// (the compiler's own choice without a bound; a bound of 1-2 CTAs lets it take 110 registers: 1.74 -> 2.35 ms)
+__global__ void __launch_bounds__(CT_THREADS, sizeof(T) == 4 ? 8 : 4) dmc_dual_verts_kernel(const T *__restrict__ mcv, Geo g, EpilogueC<T> epi,
                                                                   const uint4 *__restrict__ E,
                                                                   const uint4 *__restrict__ P,
                                                                   const unsigned short *__restrict__ C,
