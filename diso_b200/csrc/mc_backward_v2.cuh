@@ -2,7 +2,7 @@
 //
 // Replaces adj_create_cell_mc_verts_kernel (cumc.cu:474-512: one thread per used cell, 2+6 atomicAdds per
 // vertex, sdf / deform re-gathered), the dense zero fills (diso/__init__.py:33,40) and the pad-backward slices;
-// it is also stage B of the DMC backward (cudualmc.cu:957-1005).
+// with GSRC = 2 / 3 it is the WHOLE DMC backward (adj_create_dmc_verts, cudualmc.cu:957-1005), one kernel as in the reference.
 //
 // Why a second design (round 2).  ncu on the first one (mc_backward_compact.cuh, kept for callers without saved
 // records) at 512^3: 290 warp instructions and 104 LSU wavefronts per 32-point chunk, issue slots 67 % and the LSU
@@ -25,8 +25,7 @@
 // summing its <= 6 incident entries found by popcount arithmetic, no read-modify-write at all.  Fewer LSU wavefronts,
 // but ~300 instructions per chunk (150 of them the per-point gather): issue-bound at 1.80 ms, slower than v1.)
 #pragma once
-#include "mc_backward_compact.cuh"   // rcp_fast, bwd_mark_kernel, BC_THREADS
-#include "tables.cuh"
+#include "mc_backward_compact.cuh"   // rcp_fast, bwd_mark_kernel
 
 namespace diso {
 
