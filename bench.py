@@ -282,6 +282,16 @@ def run_slab_leg(rank, world, dev, n=1024, steps=3, warmup=2):
     import torch.distributed as dist
     import diso_b200
     from diso_b200 import parallel
+    # pre-flight, agreed on by all ranks (a rank that failed alone inside the sharded step would leave the others waiting in
+    # a collective): enough free memory for the slab step here, and for the unsharded comparison on rank 0
+    free, _ = torch.cuda.mem_get_info()
+    need = (100e9 * (n / 1024.0) ** 3) / world + 8e9
+    if rank == 0:
+        need = max(need, 100e9 * (n / 1024.0) ** 3)
+    ok = torch.tensor([1 if free >= need else 0], dtype=torch.int64, device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 0:
+        return {"skipped": "not enough free device memory for the %d^3 slab leg (rank %d: %.0f GB free)" % (n, rank, free / 1e9)}
     xa, xb = parallel.plan_slabs(n, world)[rank]
     sdf, deform = _slab_layers(dev, n, xa, xb)
     sf, df = parallel.SlabField(sdf, rank, world), parallel.SlabField(deform, rank, world)
