@@ -132,7 +132,8 @@ class _Extract(Function):
         # saved edge records (include/diso_b200.h: edge_rec): only when a gradient can be asked for later
         rec = None
         if ctx.needs_input_grad[0] or (deform is not None and ctx.needs_input_grad[1]):
-            rec = torch.empty((_blocks32(n_edges), 5 if alg == _lib.ALG_MC else 6, 32), dtype=grid.dtype, device=grid.device)
+            ncomp = (5 if deform is not None else 2) + (0 if alg == _lib.ALG_MC else 1)   # {p1 - p0, d0, d1} | {d0, d1}, + quad meta
+            rec = torch.empty((_blocks32(n_edges), ncomp, 32), dtype=grid.dtype, device=grid.device)
         args = (grid.data_ptr(), _ptr(deform), _DTYPES[grid.dtype], X, Y, Z, float(isovalue), state.data_ptr(),
                 ctypes.cast(ctx.counts, ctypes.c_void_p), int(bool(normalize)), _lib.frame_ptr(ctx.frame))
         if alg == _lib.ALG_MC:

@@ -281,8 +281,8 @@ int mc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const 
     kernel_attrs(reinterpret_cast<const void *>(edge_verts_kernel<T, true>), "DISO_CARVEOUT_EV", -1);
     kernel_attrs(reinterpret_cast<const void *>(edge_verts_kernel<T, false>), "DISO_CARVEOUT_EV", -1);
     if (te.ctas) {
-        if (te.list) LAUNCH("mc_emit_verts", st, (edge_verts_kernel<T, true><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, te.n_active, verts, rec, 5)));
-        else LAUNCH("mc_emit_verts", st, (edge_verts_kernel<T, false><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, te.n_active, verts, rec, 5)));
+        if (te.list) LAUNCH("mc_emit_verts", st, (edge_verts_kernel<T, true><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, te.n_active, verts, rec, deform ? 5 : 2)));
+        else LAUNCH("mc_emit_verts", st, (edge_verts_kernel<T, false><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, epi, p.E, te.list, te.n_active, verts, rec, deform ? 5 : 2)));
     }
     if (tc.ctas) {
         const uint2 *F = reinterpret_cast<const uint2 *>(p.aux);
@@ -317,15 +317,15 @@ int dmc_emit_impl(const T *sdf, const T *deform, const Geo &g, double iso, const
         if (fr.id_offset != 0) LAUNCH("dmc_emit_cross_quads", st, (dmc_emit_fused_kernel<T, true><<<2 * te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.S, p.E, P, p.C, fr.id_offset, scratch, rec, quads)));
         else LAUNCH("dmc_emit_cross_quads", st, (dmc_emit_fused_kernel<T, false><<<2 * te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.S, p.E, P, p.C, fr.id_offset, scratch, rec, quads)));
     } else if (te.ctas) {
-        if (te.list) LAUNCH("dmc_edge_crossings", st, (edge_verts_kernel<T, true><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch, rec, 6)));
-        else LAUNCH("dmc_edge_crossings", st, (edge_verts_kernel<T, false><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch, rec, 6)));
+        if (te.list) LAUNCH("dmc_edge_crossings", st, (edge_verts_kernel<T, true><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch, rec, deform ? 6 : 3)));
+        else LAUNCH("dmc_edge_crossings", st, (edge_verts_kernel<T, false><<<te.ctas, CT_THREADS, 0, st>>>(sdf, deform, g, isoT, padv, raw, p.E, te.list, te.n_active, scratch, rec, deform ? 6 : 3)));
     }
     if (tc.ctas) {
         if (tc.list) LAUNCH("dmc_emit_verts", st, (dmc_dual_verts_kernel<T, true><<<tc.ctas, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, tc.list, tc.n_active, verts)));
         else LAUNCH("dmc_emit_verts", st, (dmc_dual_verts_kernel<T, false><<<tc.ctas, CT_THREADS, 0, st>>>(scratch, g, epic, p.E, P, p.C, tc.list, tc.n_active, verts)));
     }
     if (te.ctas && !fuse_cq) {
-#define DISO_QUADS(LISTED, OFFSET, DIAG) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, LISTED, OFFSET, DIAG><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, fr.id_offset, quads, nullptr, 0, verts, qflags, rec)))
+#define DISO_QUADS(LISTED, OFFSET, DIAG) LAUNCH("dmc_emit_quads", st, (dmc_edges2_kernel<T, 0, LISTED, OFFSET, DIAG><<<te.ctas, CT_THREADS, 0, st>>>(g, p.S, p.E, P, p.C, te.list, te.n_active, T(1), T(1), T(1), nullptr, fr.id_offset, quads, nullptr, deform ? 6 : 3, verts, qflags, rec)))
         if (qflags) {
             if (fr.id_offset != 0) { if (te.list) DISO_QUADS(true, true, true); else DISO_QUADS(false, true, true); }
             else                   { if (te.list) DISO_QUADS(true, false, true); else DISO_QUADS(false, false, true); }

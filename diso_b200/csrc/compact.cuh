@@ -210,9 +210,12 @@ __device__ __forceinline__ void edge_verts_tile(EvSmem &sm, int tile, const T *_
             // saved for the backward (mc_backward_v2.cuh): everything adjComputeMcVert (cumc.cu:412-453) needs of this
             // edge, as five arrays indexed by rank -- coalesced here and there, no sdf / deform gathers in the backward
             // (groups of 32 edges, component-major inside a group: mc_backward_v2.cuh:blk_index)
-            T *r = rec + (rank >> 5) * (size_t)(32 * rec_ncomp) + (rank & 31);   // rec_ncomp: 5 (MC) or 6 (DMC: + quad meta)
+            // rec_ncomp = (deform ? 5 : 2) + (DMC: quad meta ? 1 : 0); without deform p1 - p0 is the edge's unit axis vector
+            // and only {d0, d1} are kept
+            T *r = rec + (rank >> 5) * (size_t)(32 * rec_ncomp) + (rank & 31);
             // streaming stores: the records are not read again before the backward (no measurable difference to plain stores)
-            st_stream(r, dp.x); st_stream(r + 32, dp.y); st_stream(r + 64, dp.z); st_stream(r + 96, d0); st_stream(r + 128, d1);
+            if (has_def) { st_stream(r, dp.x); st_stream(r + 32, dp.y); st_stream(r + 64, dp.z); r += 96; }
+            st_stream(r, d0); st_stream(r + 32, d1);
         }
     }
 }
@@ -393,7 +396,7 @@ __global__ void __launch_bounds__(CT_THREADS) mc_emit_fused_kernel(const T *__re
     __shared__ union U { EvSmem ev; TriSmem<false> tri; __device__ U() {} } sm;
     const int tile = blockIdx.x >> 1;
     if (blockIdx.x & 1) mc_tris_tile<false, OFFSET>(sm.tri, tile, g, E, F, C, nullptr, g.NCH, id_offset, tris);
-    else edge_verts_tile<T, false>(sm.ev, tile, sdf, deform, g, iso, padv, epi, E, nullptr, g.NCH, verts, rec, 5);
+    else edge_verts_tile<T, false>(sm.ev, tile, sdf, deform, g, iso, padv, epi, E, nullptr, g.NCH, verts, rec, deform ? 5 : 2);
 }
 
 }  // namespace diso

@@ -41,6 +41,8 @@ __device__ __forceinline__ void dmc_edges2_tile(QuadSmem<T, LISTED> &sm, int til
                                                 const T *__restrict__ verts, unsigned char *__restrict__ qflags,
                                                 T *__restrict__ rec)
 {
+    // gedge_soa: MODE 1/2 = layout of gedge (1: blocked SoA); MODE 0 = components per saved edge record (6 with deform, 3 without:
+    // the meta word is the last one)
     unsigned short *s_list = sm.list;
     unsigned *s_case = sm.cases, *s_plen = sm.plen, *s_quad = sm.quad;
     T *s_inv = sm.inv;
@@ -93,7 +95,7 @@ __device__ __forceinline__ void dmc_edges2_tile(QuadSmem<T, LISTED> &sm, int til
         if (MODE == 0) {
             // saved for the backward (6th record component, mc_backward_v2.cuh): with the quad's four ids the adjoint of
             // the dual-vertex averaging needs no cell / patch lookups at all
-            if (rec) reinterpret_cast<unsigned *>(rec + (rank >> 5) * 192 + 160 + (rank & 31))[0] = meta;
+            if (rec) reinterpret_cast<unsigned *>(rec + (rank >> 5) * (size_t)(32 * gedge_soa) + 32 * (gedge_soa - 1) + (rank & 31))[0] = meta;
             if (DIAG) {   // local ids index the local vertex array (the slab offset is added below)
                 Vec3<T> v[4];
 #pragma unroll
@@ -147,10 +149,10 @@ __global__ void __launch_bounds__(CT_THREADS) dmc_emit_fused_kernel(const T *__r
     __shared__ union U { EvSmem ev; QuadSmem<T, false> quad; __device__ U() {} } sm;
     const int tile = blockIdx.x >> 1;
     if (blockIdx.x & 1)
-        dmc_edges2_tile<T, 0, false, OFFSET, false>(sm.quad, tile, g, S, E, P, C, nullptr, g.NCH, T(1), T(1), T(1), nullptr, id_offset, quads, nullptr, 0,
-                                                   nullptr, nullptr, rec);
+        dmc_edges2_tile<T, 0, false, OFFSET, false>(sm.quad, tile, g, S, E, P, C, nullptr, g.NCH, T(1), T(1), T(1), nullptr, id_offset, quads, nullptr,
+                                                   deform ? 6 : 3, nullptr, nullptr, rec);
     else
-        edge_verts_tile<T, false>(sm.ev, tile, sdf, deform, g, iso, padv, raw, E, nullptr, g.NCH, scratch, rec, 6);
+        edge_verts_tile<T, false>(sm.ev, tile, sdf, deform, g, iso, padv, raw, E, nullptr, g.NCH, scratch, rec, deform ? 6 : 3);
 }
 
 }  // namespace diso

@@ -244,13 +244,16 @@ __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T 
                 if (axis == 1) rank += bit(r4.y, j);
             }
             T gx, gy, gz;
-            constexpr int NREC = GSRC >= 1 ? 6 : 5;   // record components per edge (DMC extractions: + the quad meta word)
+            // record components per edge: {p1 - p0 (x, y, z), d0, d1} with deform, {d0, d1} without (p1 - p0 = the unit axis
+            // vector); DMC extractions: + the quad meta word
+            constexpr int NBASE = HAS_DEF ? 5 : 2;
+            constexpr int NREC = NBASE + (GSRC >= 1 ? 1 : 0);
             const T *rp = rec + blk_index<NREC>(rank);
             if constexpr (DMC) {
                 // stage A of adj_create_dmc_verts (cudualmc.cu:957-1005): same operations and order as dmc_edges2_kernel<1|2>
                 const longlong2 *qp = reinterpret_cast<const longlong2 *>(dmc.quads + (size_t)rank * 4);
                 const longlong2 qa = __ldg(qp), qb = __ldg(qp + 1);
-                const unsigned meta = __ldg(reinterpret_cast<const unsigned *>(rp + 160));
+                const unsigned meta = __ldg(reinterpret_cast<const unsigned *>(rp + 32 * NBASE));
                 const long long id[4] = {qa.x, qa.y, qb.x, qb.y};
                 Vec3<T> acc{T(0), T(0), T(0)};
 #pragma unroll
@@ -270,8 +273,12 @@ __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T 
                 else { const T *gp = gsrc + (size_t)rank * 3; gx = __ldg(gp); gy = __ldg(gp + 1); gz = __ldg(gp + 2); }
                 gx = gx * ix; gy = gy * iy; gz = gz * iz;
             }
-            const T dpx = __ldg(rp), dpy = __ldg(rp + 32), dpz = __ldg(rp + 64), d0 = __ldg(rp + 96), d1 = __ldg(rp + 128);
+            const T d0 = __ldg(rp + 32 * (NBASE - 2)), d1 = __ldg(rp + 32 * (NBASE - 1));
             // adjComputeMcVert (cumc.cu:412-453) with one reciprocal: (iso - d1) / (d1 - d0)^2 * adj_t etc.
+            // without deform p1 - p0 is the unit axis vector (not stored); the full dot product is kept so that a non-finite
+            // gradient scale (normalize with a 1-point dimension: 1 / (dims - 1) = inf) propagates as in the reference
+            T dpx = T(axis == 0), dpy = T(axis == 1), dpz = T(axis == 2);
+            if constexpr (HAS_DEF) { dpx = __ldg(rp); dpy = __ldg(rp + 32); dpz = __ldg(rp + 64); }
             T adj_t = dpx * gx;
             adj_t = fma_rn(dpy, gy, adj_t);
             adj_t = fma_rn(dpz, gz, adj_t);

@@ -110,12 +110,14 @@ int diso_b200_read_counts(const void *state, int64_t *counts_host, void *stream)
  * proportional to the surface, not the volume).  NULL = visit every chunk.
  *
  * edge_rec (ABI v3, may be NULL): caller-owned, NCOMP * 32 * ceil(edge_rec_stride / 32) elements of dtype with
- * edge_rec_stride >= #crossing edges (groups of 32 edges, component-major inside a group); NCOMP = 5 for
- * diso_b200_mc_emit and 6 for diso_b200_dmc_emit (the 6th word per edge holds the quad's patch lengths).  When given, the edge pass also SAVES, per crossing edge and indexed by its rank (== its MC vertex id ==
- * its DMC quad id), what the adjoint of computeMcVert needs (adjComputeMcVert, cumc.cu:412-453): p1 - p0 (x, y, z),
- * d0, d1.  Passing the same buffer to *_backward selects the saved-record backward, which reads neither sdf nor
- * deform; the reference instead re-runs the whole forward inside backward
- * (diso/__init__.py:32,86).  20 (fp32) / 40 (fp64) bytes per crossing edge; callers that never differentiate pass NULL. */
+ * edge_rec_stride >= #crossing edges (groups of 32 edges, component-major inside a group); NCOMP = 5 with deform, 2 when
+ * deform is NULL, plus 1 for diso_b200_dmc_emit (the last word per edge holds the quad's patch lengths).  When given,
+ * the edge pass also SAVES, per crossing edge and indexed by its rank (== its MC vertex id == its DMC quad id), what the
+ * adjoint of computeMcVert needs (adjComputeMcVert, cumc.cu:412-453): p1 - p0 (x, y, z), d0, d1 -- without deform p1 - p0
+ * is the edge's unit axis vector and only d0, d1 are kept.  Passing the same buffer (and the same deform / NULL) to
+ * *_backward selects the saved-record backward, which reads neither sdf nor deform; the reference instead re-runs the
+ * whole forward inside backward (diso/__init__.py:32,86).  20 / 8 bytes (fp32; fp64: twice that) per crossing edge;
+ * callers that never differentiate pass NULL. */
 int diso_b200_mc_emit(const void *sdf, const void *deform, int dtype, int X, int Y, int Z,
                       double iso, const void *state, const int64_t *counts_host, int normalize,
                       const diso_b200_frame *frame, void *verts, int64_t *tris, void *edge_rec,

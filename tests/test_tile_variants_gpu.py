@@ -29,13 +29,15 @@ def blobs(n, seed):
 
 @pytest.mark.parametrize("alg", ["mc", "dmc"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-def test_dense_and_listed_tiles_agree(alg, dtype):
+@pytest.mark.parametrize("use_def", [True, False])
+def test_dense_and_listed_tiles_agree(alg, dtype, use_def):
     import diso_b200
     from diso_b200 import _lib
     L = _lib.load()
     n = 70
     sdf = blobs(n, 3).to(dtype).to(DEV)
-    deform = (0.4 * torch.tanh(torch.randn(n, n, n, 3, generator=torch.Generator().manual_seed(5)))).to(dtype).to(DEV)
+    deform = (0.4 * torch.tanh(torch.randn(n, n, n, 3, generator=torch.Generator().manual_seed(5)))).to(dtype).to(DEV) if use_def else None
+    dptr = lambda t: None if t is None else t.data_ptr()
     alg_id = _lib.ALG_MC if alg == "mc" else _lib.ALG_DMC
     dt = _lib.F32 if dtype == torch.float32 else _lib.F64
     state, counts = diso_b200._count(alg_id, sdf, 0.0)
@@ -55,29 +57,31 @@ def test_dense_and_listed_tiles_agree(alg, dtype):
             verts = torch.full((nv, 3), float("nan"), dtype=dtype, device=DEV)
             faces = torch.full((nf, k), -1, dtype=torch.int64, device=DEV)
             adj_s = torch.full_like(sdf, float("nan"))
-            adj_d = torch.full_like(deform, float("nan"))
-            ncomp = 5 if alg == "mc" else 6
+            adj_d = torch.full_like(deform, float("nan")) if use_def else None
+            ncomp = (5 if use_def else 2) + (0 if alg == "mc" else 1)      # include/diso_b200.h: edge_rec
             rec = torch.full(((ne + 31) // 32, ncomp, 32), float("nan"), dtype=dtype, device=DEV) if use_rec else None
             rp = rec.data_ptr() if use_rec else None
             w = torch.cos(torch.arange(nv * 3, dtype=torch.float64).reshape(nv, 3) * 0.618).to(dtype).to(DEV)
-            common = (sdf.data_ptr(), deform.data_ptr(), dt, n, n, n, 0.0, state.data_ptr())
+            common = (sdf.data_ptr(), dptr(deform), dt, n, n, n, 0.0, state.data_ptr())
+            keep = lambda: [adj_s.clone()] + ([adj_d.clone()] if use_def else [])
             grads = []
             if alg == "mc":
                 _lib.check(L.diso_b200_mc_emit(*common, ch, 1, None, verts.data_ptr(), faces.data_ptr(), rp, ne, st))
-                _lib.check(L.diso_b200_mc_backward(*common, ch, w.data_ptr(), 1, None, rp, ne, adj_s.data_ptr(), adj_d.data_ptr(), st))
-                grads += [adj_s.clone(), adj_d.clone()]
+                _lib.check(L.diso_b200_mc_backward(*common, ch, w.data_ptr(), 1, None, rp, ne, adj_s.data_ptr(), dptr(adj_d), st))
+                grads += keep()
             else:
                 scratch = torch.empty(((ne + 31) // 32 * 32, 3), dtype=dtype, device=DEV)
                 _lib.check(L.diso_b200_dmc_emit(*common, ch, 1, None, scratch.data_ptr(), verts.data_ptr(), faces.data_ptr(), rp, ne, None, st))
                 for gm in (_lib.GRAD_REFERENCE, _lib.GRAD_EXACT):
-                    _lib.check(L.diso_b200_dmc_backward(*common, ch, w.data_ptr(), 1, None, gm, rp, ne, faces.data_ptr() if use_rec else None, scratch.data_ptr(), adj_s.data_ptr(), adj_d.data_ptr(), st))
-                    grads += [adj_s.clone(), adj_d.clone()]
+                    _lib.check(L.diso_b200_dmc_backward(*common, ch, w.data_ptr(), 1, None, gm, rp, ne, faces.data_ptr() if use_rec else None, scratch.data_ptr(), adj_s.data_ptr(), dptr(adj_d), st))
+                    grads += keep()
             torch.cuda.synchronize()
             if use_rec:
-                flat = rec.permute(1, 0, 2).reshape(ncomp, -1)[:5, :ne]
+                flat = rec.permute(1, 0, 2).reshape(ncomp, -1)[:(5 if use_def else 2), :ne]
                 assert bool(torch.isfinite(flat).all()), "edge records not fully written"
             res.append([t.cpu().numpy() for t in [verts, faces] + grads])
-        for a, b, what in zip(res[0], res[1], ("verts", "faces", "adj_sdf", "adj_deform", "adj_sdf(exact)", "adj_deform(exact)")):
+        names = ("adj_sdf", "adj_deform", "adj_sdf(exact)", "adj_deform(exact)") if use_def else ("adj_sdf", "adj_sdf(exact)")
+        for a, b, what in zip(res[0], res[1], ("verts", "faces") + names):
             assert not np.isnan(a.astype(np.float64)).any() and (a != -1).any(), what + ": not fully written"
             assert np.array_equal(a, b), what + ": listed and dense tile flavours differ (records: %s)" % use_rec
         per_path[use_rec] = res[0]
