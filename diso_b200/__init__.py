@@ -28,7 +28,15 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """cudaStream_t of the current device's current stream.  torch.cuda.current_stream() builds a Stream object through several
+    layers of device-index helpers (~8 us a time, three times per forward+backward: a tenth of a 64^3 extraction,
+    tools/host_profile.py); the raw getter is one C call."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -212,8 +220,7 @@ def _run(alg, dtype, grad_mode, grid, deform, isovalue, normalize, want_state=Fa
     with _on(grid.device):
         g = grid.contiguous()
         d = deform.contiguous() if deform is not None else None
-        with torch.no_grad():
-            state, counts = _count(alg, g, isovalue)
+        state, counts = _count(alg, g, isovalue)     # allocates and launches only: nothing autograd could record
         n_verts, n_faces = counts[_lib.CNT_VERTS], counts[_lib.CNT_FACES]
         # diso/__init__.py:49-50,103-104: empty-surface early-out (min >= iso or max <= iso),
         # which returns detached (0,3) verts and INT32 (0,3)/(0,4) faces.
