@@ -36,6 +36,21 @@ constexpr int B2_WARPS = B2_THREADS / 32;
 // element (rank, comp) of an NCOMP-component array lives at (rank / 32) (32 NCOMP) + 32 comp + rank % 32.  A warp
 // touching 32 consecutive ranks reads / writes full 128-byte lines per component, and a thread needs ONE address for
 // all of its components (the others are immediate offsets).
+// experiment knob (build variants): how the read-once record / quad loads are issued.  Measured at 512^3 (mc / dmc backward):
+// ld.global.nc 1.442 / 2.247 ms, ld.global.cs 1.467 / 2.304, ld.global.lu 1.457 / 2.290 -- the plain read-only path stays.
+#ifndef DISO_REC_LD
+#define DISO_REC_LD 0
+#endif
+template <typename T> __device__ __forceinline__ T ld_once(const T *p)
+{
+#if DISO_REC_LD == 1
+    return __ldcs(p);
+#elif DISO_REC_LD == 2
+    return __ldlu(p);
+#else
+    return __ldg(p);
+#endif
+}
 template <int NCOMP> __device__ __forceinline__ size_t blk_index(size_t rank) { return (rank >> 5) * (32 * NCOMP) + (rank & 31); }
 
 template <typename T> struct alignas(4 * sizeof(T)) Quad { T d, x, y, z; };
@@ -252,8 +267,8 @@ __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T 
             if constexpr (DMC) {
                 // stage A of adj_create_dmc_verts (cudualmc.cu:957-1005): same operations and order as dmc_edges2_kernel<1|2>
                 const longlong2 *qp = reinterpret_cast<const longlong2 *>(dmc.quads + (size_t)rank * 4);
-                const longlong2 qa = __ldg(qp), qb = __ldg(qp + 1);
-                const unsigned meta = __ldg(reinterpret_cast<const unsigned *>(rp + 32 * NBASE));
+                const longlong2 qa = ld_once(qp), qb = ld_once(qp + 1);
+                const unsigned meta = ld_once(reinterpret_cast<const unsigned *>(rp + 32 * NBASE));
                 const long long id[4] = {qa.x, qa.y, qb.x, qb.y};
                 Vec3<T> acc{T(0), T(0), T(0)};
 #pragma unroll
@@ -273,12 +288,12 @@ __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T 
                 else { const T *gp = gsrc + (size_t)rank * 3; gx = __ldg(gp); gy = __ldg(gp + 1); gz = __ldg(gp + 2); }
                 gx = gx * ix; gy = gy * iy; gz = gz * iz;
             }
-            const T d0 = __ldg(rp + 32 * (NBASE - 2)), d1 = __ldg(rp + 32 * (NBASE - 1));
+            const T d0 = ld_once(rp + 32 * (NBASE - 2)), d1 = ld_once(rp + 32 * (NBASE - 1));
             // adjComputeMcVert (cumc.cu:412-453) with one reciprocal: (iso - d1) / (d1 - d0)^2 * adj_t etc.
             // without deform p1 - p0 is the unit axis vector (not stored); the full dot product is kept so that a non-finite
             // gradient scale (normalize with a 1-point dimension: 1 / (dims - 1) = inf) propagates as in the reference
             T dpx = T(axis == 0), dpy = T(axis == 1), dpz = T(axis == 2);
-            if constexpr (HAS_DEF) { dpx = __ldg(rp); dpy = __ldg(rp + 32); dpz = __ldg(rp + 64); }
+            if constexpr (HAS_DEF) { dpx = ld_once(rp); dpy = ld_once(rp + 32); dpz = ld_once(rp + 64); }
             T adj_t = dpx * gx;
             adj_t = fma_rn(dpy, gy, adj_t);
             adj_t = fma_rn(dpz, gz, adj_t);
