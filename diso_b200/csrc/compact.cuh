@@ -280,6 +280,25 @@ __device__ __forceinline__ unsigned edge_rank(const RecCache<LISTED> &rc, int cl
     return r;
 }
 
+// the same for a pre-decoded corner code f = {row set : 2, dz : 1, axis >= 1 : 1, axis == 2 : 1} (T_MC_TRI5, tools/extract_tables.py):
+// the axis bits extend the "points before lane jj" mask by lane jj itself for the x- (and y-) crossing planes, so the rank is
+// base + three popcounts with no per-axis selects.  The triangle kernel is bound by the integer ALU pipe (83 % busy,
+// profiles/r2_emit_pipes.md); this form needs ~25 instead of ~36 instructions per corner.
+template <bool LISTED>
+__device__ __forceinline__ unsigned corner_rank(const RecCache<LISTED> &rc, int cl, int j, unsigned f)
+{
+    const int rs = f & 3u;
+    int jj = j + (int)((f >> 2) & 1u);
+    const int nxt = jj >> 5;     // dz = 1 from lane 31: first point of the following chunk
+    jj &= 31;
+    uint4 rec;
+    if (LISTED && nxt && !rc.contig) rec = __ldg(rc.E + rc.s_k[cl] + 1 + (rs >> 1) * rc.sX + (rs & 1) * rc.sY);
+    else rec = rc.s_E[rs * (CT_CHUNKS + 1) + cl + nxt];
+    const unsigned l = lanemask_lt(jj);
+    const unsigned lx = l | (((f >> 3) & 1u) << jj), ly = l | ((f >> 4) << jj);
+    return rec.x + __popc(rec.y & lx) + __popc(rec.z & ly) + __popc(rec.w & l);
+}
+
 // ------------------------------------------------------------------------------------------
 // K4 (v3): triangles, triangle-parallel.  Replaces count_cell_mc_tris / create_cell_mc_tris
 // (cumc.cu:540-612) + the int64 widening (diso/__init__.py:61).
@@ -294,7 +313,7 @@ constexpr int CT_MAX_TRIS = CT_CHUNKS * 160;
 // OFFSET: add id_offset to every index (slab -> global ids); a separate instantiation keeps the 64-bit adds
 // out of the standalone kernel (they cost 2.5 % there).
 template <bool LISTED> struct TriSmem {
-    unsigned long long cases[256];
+    unsigned tri5[1024];     // T_MC_TRI5: per case {tris 0|1, tris 2|3, tri 4, #tris}
     uint4 recs[CT_RECS];
     unsigned short list[CT_MAX_TRIS];
     __align__(8) unsigned char code[CT_CHUNKS * 32];
@@ -307,7 +326,7 @@ __device__ __forceinline__ void mc_tris_tile(TriSmem<LISTED> &sm, int tile, cons
                                              const unsigned *__restrict__ alist, int n_active,
                                              long long id_offset, long long *__restrict__ tris)
 {
-    unsigned long long *s_case = sm.cases;
+    unsigned *s_tri = sm.tri5;
     uint4 *s_E = sm.recs;
     unsigned short *s_list = sm.list;
     unsigned char *s_code = sm.code;
@@ -316,7 +335,8 @@ __device__ __forceinline__ void mc_tris_tile(TriSmem<LISTED> &sm, int tile, cons
     const unsigned tile_base = F[tr.kfirst].x;
     const unsigned n = F[tr.klast + 1].x - tile_base;
     if (n == 0) return;
-    s_case[threadIdx.x] = T_MC_CASE[threadIdx.x];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s_tri[i * CT_THREADS + threadIdx.x] = T_MC_TRI5[i * CT_THREADS + threadIdx.x];
     if (LISTED) {
         if ((int)threadIdx.x < tr.count) s_k[threadIdx.x] = tr.chunk(threadIdx.x);
     }
@@ -341,7 +361,7 @@ __device__ __forceinline__ void mc_tris_tile(TriSmem<LISTED> &sm, int tile, cons
                         const unsigned info = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
                         const unsigned code = info & 0xffu;
                         if (j < 4) codes_lo |= code << (8 * j); else codes_hi |= code << (8 * (j - 4));
-                        const unsigned nt = reinterpret_cast<const unsigned *>(s_case)[2 * code + 1] >> 28;
+                        const unsigned nt = s_tri[4 * code + 3];
                         const unsigned slot = tb + (info >> 8);
                         const unsigned dd = dbase | ((unsigned)j << 3);
 #pragma unroll
@@ -359,10 +379,10 @@ __device__ __forceinline__ void mc_tris_tile(TriSmem<LISTED> &sm, int tile, cons
         const unsigned d = s_list[i];
         const unsigned q = d & 7u;
         const int j = (d >> 3) & 31, cl = (d >> 8) & 63;
-        const unsigned tri = (unsigned)(s_case[s_code[cl * 32 + j]] >> (12 * q)) & 0xfffu;
-        long long a = edge_rank<LISTED>(rc, cl, j, tri & 15u);
-        long long b = edge_rank<LISTED>(rc, cl, j, (tri >> 4) & 15u);
-        long long c = edge_rank<LISTED>(rc, cl, j, tri >> 8);
+        const unsigned tri = (s_tri[4 * s_code[cl * 32 + j] + (q >> 1)] >> (15 * (q & 1u))) & 0x7fffu;
+        long long a = corner_rank<LISTED>(rc, cl, j, tri & 31u);
+        long long b = corner_rank<LISTED>(rc, cl, j, (tri >> 5) & 31u);
+        long long c = corner_rank<LISTED>(rc, cl, j, tri >> 10);
         if (OFFSET) { a += id_offset; b += id_offset; c += id_offset; }
         long long *dst = tris + (size_t)(tile_base + i) * 3;
         st_stream(dst, a); st_stream(dst + 1, b); st_stream(dst + 2, c);

@@ -87,3 +87,24 @@ def test_table_structure_assumptions():
     for name, val in (("EDGE_DX", dx), ("EDGE_DY", dy), ("EDGE_DZ", dz), ("EDGE_AX", ax)):
         m = re.search(name + r" = (0x[0-9a-f]+)u", src)
         assert int(m.group(1), 16) == val, name
+
+
+def test_decoded_triangle_table_consistent_with_oracle_tables():
+    """T_MC_TRI5 (the triangle kernel's pre-decoded corner codes) against the triangle list and the edge geometry table
+    (mcEdgeLocations, cumc.cu:109-122: per local edge {dx, dy, dz, axis} of the owning point)."""
+    t = _parse(os.path.join(ROOT, "oracle", "diso_tables.h"))
+    k = _parse(os.path.join(ROOT, "diso_b200", "csrc", "case_tables.inc"))
+    mf, mi, loc, tri5 = t["T_MC_FIRST"], t["T_MC_IDS"], t["T_EDGE_LOC"], k["T_MC_TRI5"]
+    assert len(tri5) == 1024
+    for code in range(256):
+        ids = mi[mf[code]:mf[code + 1]]
+        assert tri5[4 * code + 3] == len(ids) // 3
+        for i, e in enumerate(ids):
+            dx, dy, dz, ax = loc[4 * e:4 * e + 4]
+            q, c = divmod(i, 3)
+            f = (tri5[4 * code + (q >> 1)] >> (15 * (q & 1) + 5 * c)) & 31
+            assert f == (2 * dx + dy) | (dz << 2) | ((ax >= 1) << 3) | ((ax == 2) << 4), (code, i, e)
+        used = 5 * len(ids)     # nothing stored beyond the case's triangles
+        for w in range(3):
+            bits = max(0, min(30, used - 30 * w))
+            assert tri5[4 * code + w] >> bits == 0

@@ -239,6 +239,25 @@ def main():
     for i in range(0, 256, 4):
         inc.append("    " + ", ".join("0x%012xull" % v for v in members[i:i + 4]) + ",")
     inc.append("};")
+    # MC triangles, decoded form for the triangle kernel (compact.cuh:mc_tris_tile): per case four 32-bit words; word w holds
+    # triangles 2w (bits 0..14) and 2w+1 (bits 15..29), word 3 the triangle count.  A triangle = three 5-bit corner codes
+    # {row set 2*dx+dy : 2, dz : 1, axis >= 1 : 1, axis == 2 : 1} of the corner's edge (csrc/tables.cuh: EDGE_DX/DY/DZ/AX) --
+    # what the kernel would otherwise decode from the 4-bit edge id with ~10 integer instructions per corner.
+    EDGE_DX, EDGE_DY, EDGE_DZ, EDGE_AX = 0x622, 0x0f0, 0xc44, 0x558888
+    tri5 = []
+    for code in range(256):
+        ids = mi[mf[code]:mf[code + 1]]
+        words = [0, 0, 0, len(ids) // 3]
+        for i, e in enumerate(ids):
+            ax = (EDGE_AX >> (2 * e)) & 3
+            f = (2 * ((EDGE_DX >> e) & 1) + ((EDGE_DY >> e) & 1)) | (((EDGE_DZ >> e) & 1) << 2) | ((1 if ax >= 1 else 0) << 3) | ((1 if ax == 2 else 0) << 4)
+            q, c = divmod(i, 3)
+            words[q >> 1] |= f << (15 * (q & 1) + 5 * c)
+        tri5 += words
+    inc.append("DISO_TABLE_QUAL unsigned int T_MC_TRI5[1024] = {")
+    for i in range(0, 1024, 8):
+        inc.append("    " + ", ".join("0x%08xu" % v for v in tri5[i:i + 8]) + ",")
+    inc.append("};")
     inc.append("DISO_TABLE_QUAL unsigned int T_DMC_QUAD[6] = {" + ", ".join("0x%08xu" % v for v in quad_pack) + "};")
     inc.append("")
     with open(os.path.join(ROOT, "diso_b200/csrc/case_tables.inc"), "w") as f:
