@@ -24,8 +24,7 @@ namespace diso {
 // instead of re-reading the 32-byte quads and chasing ids -> vertices (2.15 ms at 512^3, latency-bound).
 template <typename T, bool LISTED> struct QuadSmem {
     unsigned short list[CT_MAX_EDGES];
-    unsigned cases[256];
-    unsigned plen[256];
+    unsigned long long edge5[256];   // T_DMC_EDGE5: per cell edge {length of its patch : 3, index of the patch in the cell : 2}
     unsigned quad[8];
     T inv[8];
     int k[LISTED ? CT_CHUNKS : 1];
@@ -44,11 +43,11 @@ __device__ __forceinline__ void dmc_edges2_tile(QuadSmem<T, LISTED> &sm, int til
     // gedge_soa: MODE 1/2 = layout of gedge (1: blocked SoA); MODE 0 = components per saved edge record (6 with deform, 3 without:
     // the meta word is the last one)
     unsigned short *s_list = sm.list;
-    unsigned *s_case = sm.cases, *s_plen = sm.plen, *s_quad = sm.quad;
+    unsigned long long *s_edge5 = sm.edge5;
+    unsigned *s_quad = sm.quad;
     T *s_inv = sm.inv;
     int *s_k = sm.k;
-    s_case[threadIdx.x] = T_DMC_CASE[threadIdx.x];
-    s_plen[threadIdx.x] = T_DMC_PATCHLEN[threadIdx.x];
+    s_edge5[threadIdx.x] = T_DMC_EDGE5[threadIdx.x];
     if (threadIdx.x < 6) s_quad[threadIdx.x] = T_DMC_QUAD[threadIdx.x];
     if (threadIdx.x < 8) s_inv[threadIdx.x] = threadIdx.x ? T(1) / T((int)threadIdx.x) : T(0);
     const TileRange<LISTED> tr(alist, n_active, tile);
@@ -78,13 +77,14 @@ __device__ __forceinline__ void dmc_edges2_tile(QuadSmem<T, LISTED> &sm, int til
             const unsigned first = P[kk].x + (info >> 8);
             const unsigned code = info & 0xffu;
             const unsigned eid = b >> 4;
-            const unsigned ord = (s_case[code] >> (2 * eid)) & 3u;
+            const unsigned f5 = (unsigned)(s_edge5[code] >> (5 * eid)) & 31u;   // {patch length : 3, patch index : 2}
+            const unsigned ord = f5 >> 3;
             if (MODE == 0) {
                 id[c] = (long long)(first + ord);
-                meta |= (((s_plen[code] >> (4 * ord)) & 7u) | (ord << 3)) << (5 * c);
+                meta |= f5 << (5 * c);
             } else {
                 const unsigned src = (MODE == 1) ? first + ord : first;
-                const T inv = s_inv[(s_plen[code] >> (4 * ord)) & 7u];
+                const T inv = s_inv[f5 & 7u];
                 const T *p = adj_dual + (size_t)src * 3;
                 acc.x = fma_rn(__ldg(p), inv, acc.x);
                 acc.y = fma_rn(__ldg(p + 1), inv, acc.y);

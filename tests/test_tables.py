@@ -108,3 +108,19 @@ def test_decoded_triangle_table_consistent_with_oracle_tables():
         for w in range(3):
             bits = max(0, min(30, used - 30 * w))
             assert tri5[4 * code + w] >> bits == 0
+
+
+def test_dmc_edge5_table_consistent_with_packed_tables():
+    """T_DMC_EDGE5 = per edge {length of its patch : 3, index of the patch in the cell : 2}, against T_DMC_CASE / T_DMC_PATCHLEN
+    (themselves checked against the oracle tables above)."""
+    k = _parse(os.path.join(ROOT, "diso_b200", "csrc", "case_tables.inc"))
+    for code in range(256):
+        w, c, e5 = k["T_DMC_CASE"][code], k["T_DMC_PATCHLEN"][code], k["T_DMC_EDGE5"][code]
+        for e in range(12):
+            f = (e5 >> (5 * e)) & 31
+            if (c >> (16 + e)) & 1:
+                o = (w >> (2 * e)) & 3
+                assert f == ((c >> (4 * o)) & 15) | (o << 3)
+            else:
+                assert f == 0
+        assert e5 >> 60 == 0

@@ -258,6 +258,21 @@ def main():
     for i in range(0, 1024, 8):
         inc.append("    " + ", ".join("0x%08xu" % v for v in tri5[i:i + 8]) + ",")
     inc.append("};")
+    # DMC, per case one 64-bit word for the quad / edge-adjoint kernels (dmc_compact.cuh:dmc_edges2_tile): bits 5e..5e+4 =
+    # {number of edges of the patch that edge e belongs to : 3, index of that patch inside the cell : 2} -- one shared-memory
+    # read per quad corner instead of T_DMC_CASE + T_DMC_PATCHLEN.
+    edge5 = []
+    for code in range(256):
+        w = 0
+        for e in range(12):
+            o = off[code * 12 + e]
+            if o >= 0:
+                w |= ((ef[pf[code] + o + 1] - ef[pf[code] + o]) | (o << 3)) << (5 * e)
+        edge5.append(w)
+    inc.append("DISO_TABLE_QUAL unsigned long long T_DMC_EDGE5[256] = {")
+    for i in range(0, 256, 4):
+        inc.append("    " + ", ".join("0x%015xull" % v for v in edge5[i:i + 4]) + ",")
+    inc.append("};")
     inc.append("DISO_TABLE_QUAL unsigned int T_DMC_QUAD[6] = {" + ", ".join("0x%08xu" % v for v in quad_pack) + "};")
     inc.append("")
     with open(os.path.join(ROOT, "diso_b200/csrc/case_tables.inc"), "w") as f:
