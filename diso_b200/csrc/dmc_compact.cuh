@@ -188,7 +188,6 @@ __global__ void __launch_bounds__(CT_THREADS, sizeof(T) == 4 ? 8 : 4) dmc_dual_v
 {
     __shared__ unsigned short s_list[CT_MAX_PATCHES];
     __shared__ __align__(16) unsigned short s_cell[CT_CHUNKS * 32];
-    __shared__ unsigned s_plen[256];
     __shared__ unsigned long long s_members[256];
     __shared__ uint4 s_E[CT_RECS];
     __shared__ T s_inv[8];
@@ -197,7 +196,6 @@ __global__ void __launch_bounds__(CT_THREADS, sizeof(T) == 4 ? 8 : 4) dmc_dual_v
     const unsigned tile_base = P[tr.kfirst].x;
     const unsigned n = P[tr.klast + 1].x - tile_base;
     if (n == 0) return;
-    s_plen[threadIdx.x] = T_DMC_PATCHLEN[threadIdx.x];
     s_members[threadIdx.x] = T_DMC_MEMBERS[threadIdx.x];
     if (threadIdx.x < 8) s_inv[threadIdx.x] = threadIdx.x ? T(1) / T((int)threadIdx.x) : T(0);
     if (LISTED) {
@@ -248,8 +246,9 @@ __global__ void __launch_bounds__(CT_THREADS, sizeof(T) == 4 ? 8 : 4) dmc_dual_v
         const unsigned q = d & 3u;
         const int j = (d >> 2) & 31, cl = (d >> 7) & 63;
         const unsigned code = s_cell[cl * 32 + j] & 0xffu;
-        const unsigned plen = s_plen[code];
-        const unsigned mm = (unsigned)(s_members[code] >> (12 * q)) & 0xfffu;  // member edges of this patch
+        const unsigned long long mw = s_members[code];                // four 12-bit member masks + four 4-bit patch lengths
+        const unsigned plen = (unsigned)(mw >> 48);
+        const unsigned mm = (unsigned)(mw >> (12 * q)) & 0xfffu;      // member edges of this patch
         Vec3<T> acc{T(0), T(0), T(0)};
         if (fast) {
             const unsigned l = lanemask_lt(j);
@@ -286,11 +285,9 @@ __global__ void __launch_bounds__(CT_THREADS, sizeof(T) == 4 ? 8 : 4) dmc_dual_v
                         vx[t] = __ldg(pv); vy[t] = __ldg(pv + 1); vz[t] = __ldg(pv + 2);
                     }
                 }
+                // unconditional: a non-member slot holds +0, and acc (started at +0, never -0) + 0 is acc bit for bit
 #pragma unroll
-                for (int t = 0; t < 6; ++t) {
-                    const int e = 6 * h + t;
-                    if ((mm >> e) & 1u) { acc.x = acc.x + vx[t]; acc.y = acc.y + vy[t]; acc.z = acc.z + vz[t]; }
-                }
+                for (int t = 0; t < 6; ++t) { acc.x = acc.x + vx[t]; acc.y = acc.y + vy[t]; acc.z = acc.z + vz[t]; }
             }
         } else {
             // scattered tile of a sparse surface: the generic per-edge decode (next-chunk records from global)

@@ -66,6 +66,7 @@ def test_packed_kernel_tables_consistent_with_oracle_tables():
         for q in range(4):
             want_m = sum(1 << e for e in range(12) if off[code * 12 + e] == q)
             assert (mem >> (12 * q)) & 0xfff == want_m
+        assert mem >> 48 == c & 0xffff      # the patch lengths ride in the top 16 bits
         assert (w >> 31) == (prob[code] != 255)
         if prob[code] != 255:
             assert (w >> 28) & 7 == prob[code]

@@ -226,7 +226,7 @@ def main():
     for i in range(0, 256, 8):
         inc.append("    " + ", ".join("0x%08xu" % v for v in dmc_cnt[i:i + 8]) + ",")
     inc.append("};")
-    # per case: four 12-bit masks (bits 12q..12q+11) = member edges of patch q
+    # per case: four 12-bit masks (bits 12q..12q+11) = member edges of patch q, + the patch lengths in the top 16 bits
     members = []
     for code in range(256):
         w = 0
@@ -234,10 +234,10 @@ def main():
             o = off[code * 12 + e]
             if o >= 0:
                 w |= 1 << (12 * o + e)
-        members.append(w)
+        members.append(w | ((dmc_cnt[code] & 0xffff) << 48))   # bits 48..63: the four patch lengths (4 x 4 bits) -- one read per dual vertex
     inc.append("DISO_TABLE_QUAL unsigned long long T_DMC_MEMBERS[256] = {")
     for i in range(0, 256, 4):
-        inc.append("    " + ", ".join("0x%012xull" % v for v in members[i:i + 4]) + ",")
+        inc.append("    " + ", ".join("0x%016xull" % v for v in members[i:i + 4]) + ",")
     inc.append("};")
     # MC triangles, decoded form for the triangle kernel (compact.cuh:mc_tris_tile): per case four 32-bit words; word w holds
     # triangles 2w (bits 0..14) and 2w+1 (bits 15..29), word 3 the triangle count.  A triangle = three 5-bit corner codes
