@@ -323,8 +323,18 @@ __device__ __forceinline__ void mc_backward2_block(const Geo &g, T iso, T ix, T 
     }
 
     // ---- 4. dense write-out: one warp per output row-chunk, lane == point ------------------------------------------
-    for (int o = wid; o < BX * BY; o += B2_WARPS) {
-        const long long rowb = s_rowb[(o / BY + 1) * (BY + 1) + o % BY + 1];   // element of lane 0
+    // Warp w owns the RPW consecutive rows o = w * RPW + it: they share one x row of the block when BY % RPW == 0, so the row's
+    // slot in s_rowb is a per-warp base + it (the strided assignment o = w + it * B2_WARPS cost a division per row: 12 of the ~55
+    // instructions of a row's write-out).
+    constexpr bool RPW_OK = (BX * BY) % B2_WARPS == 0 && BY % ((BX * BY) / B2_WARPS ? (BX * BY) / B2_WARPS : 1) == 0;
+    constexpr int RPW = RPW_OK ? (BX * BY) / B2_WARPS : 1;
+    const int o0 = RPW_OK ? wid * RPW : wid;
+    const int slot0 = (o0 / BY + 1) * (BY + 1) + o0 % BY + 1;
+#pragma unroll
+    for (int it = 0; it < (RPW_OK ? RPW : (BX * BY + B2_WARPS - 1) / B2_WARPS); ++it) {
+        const int o = RPW_OK ? o0 + it : wid + it * B2_WARPS;
+        if (!RPW_OK && o >= BX * BY) break;
+        const long long rowb = s_rowb[RPW_OK ? slot0 + it : (o / BY + 1) * (BY + 1) + o % BY + 1];   // element of lane 0
         if (rowb < -1) continue;                                                // row outside the grid
         Ent acc;
         if constexpr (HAS_DEF && sizeof(T) == 4) {
